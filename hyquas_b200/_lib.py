@@ -1,0 +1,91 @@
+"""ctypes binding of libhyquas_b200.so (the C-ABI in include/hyquas_b200.h and hyquas_b200_circuit.h).
+
+There is no fallback: if the shared library is missing or a symbol is absent, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhyquas_b200.so")
+
+
+class HqGate(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int32), ("target", ctypes.c_int32), ("control", ctypes.c_int32),
+                ("control2", ctypes.c_int32), ("mat", ctypes.c_double * 8)]
+
+
+class HyquasError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C hyquas_b200/csrc` (or __graft_entry__.build()); "
+            "hyquas_b200 has no CPU fallback")
+    return ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+
+
+lib = _load()
+
+_c = ctypes
+_P = _c.POINTER
+_SIGS = {
+    # device layer -- include/hyquas_b200.h
+    "hq_last_error": (_c.c_char_p, []),
+    "hq_version": (_c.c_char_p, []),
+    "hq_device_count": (_c.c_int, [_P(_c.c_int)]),
+    "hq_init": (_c.c_int, [_c.c_int]),
+    "hq_shutdown": (_c.c_int, []),
+    "hq_sync": (_c.c_int, []),
+    "hq_device_info": (_c.c_int, [_c.c_char_p, _c.c_size_t, _P(_c.c_int), _P(_c.c_size_t)]),
+    "hq_state_alloc": (_c.c_int, [_c.c_int, _P(_c.c_void_p)]),
+    "hq_state_free": (_c.c_int, [_c.c_void_p]),
+    "hq_state_init": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int]),
+    "hq_state_download": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p]),
+    "hq_state_upload": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p]),
+    "hq_amp_fetch": (_c.c_int, [_c.c_void_p, _c.c_int64, _P(_c.c_double)]),
+    "hq_dump_scan": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_int64, _P(_c.c_int64)]),
+    "hq_state_norm2": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
+    "hq_group_tile_bits": (_c.c_int, []),
+    "hq_group_min_run_bits": (_c.c_int, []),
+    "hq_group_plan_create": (_c.c_int, [_c.c_int, _c.c_uint64, _P(HqGate), _c.c_int, _P(_c.c_void_p)]),
+    "hq_group_plan_launch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int]),
+    "hq_group_plan_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
+    "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
+    "hq_timer_start": (_c.c_int, []),
+    "hq_timer_stop_ms": (_c.c_int, [_P(_c.c_float)]),
+    # circuit layer -- include/hyquas_b200_circuit.h
+    "hq_circuit_last_error": (_c.c_char_p, []),
+    "hq_runtime_init": (_c.c_int, []),
+    "hq_runtime_init_host_only": (_c.c_int, [_c.c_int, _c.c_int]),
+    "hq_circuit_create": (_c.c_int, [_c.c_int, _P(_c.c_void_p)]),
+    "hq_circuit_from_qasm": (_c.c_int, [_c.c_char_p, _P(_c.c_void_p)]),
+    "hq_circuit_add_gate": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P(_c.c_double), _c.c_int]),
+    "hq_circuit_num_qubits": (_c.c_int, [_c.c_void_p]),
+    "hq_circuit_num_gates": (_c.c_int, [_c.c_void_p]),
+    "hq_circuit_compile": (_c.c_int, [_c.c_void_p]),
+    "hq_circuit_plan_only": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_circuit_run": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_double)]),
+    "hq_circuit_schedule_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_circuit_dump": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _P(_c.c_size_t)]),
+    "hq_circuit_amplitudes": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_circuit_logger_flush": (_c.c_int, [_c.c_char_p, _c.c_size_t]),
+    "hq_circuit_destroy": (_c.c_int, [_c.c_void_p]),
+    # test hook (device/plan_emulator.cpp) -- used by the CPU test-suite only
+    "hq_debug_group_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+}
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)      # AttributeError here == the library does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib.hq_last_error().decode() or lib.hq_circuit_last_error().decode()
+        raise HyquasError(f"hyquas_b200 error {rc}: {msg}")

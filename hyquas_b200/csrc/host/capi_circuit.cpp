@@ -1,0 +1,177 @@
+// Circuit-level C-ABI (declared in include/hyquas_b200_circuit.h): lets non-C++ hosts (the ctypes tests,
+// bench.py) drive exactly the code path `hyquas_main` runs: parse / addGate -> compile -> run -> dump.
+#include <cstring>
+#include <memory>
+
+#include "circuit.h"
+#include "hyquas_b200_circuit.h"
+#include "logger.h"
+#include "qasm.h"
+#include "compiler.h"
+
+struct hq_circuit {
+    std::unique_ptr<Circuit> c;
+    std::string dump;
+};
+
+static thread_local std::string g_cerr;
+extern "C" const char* hq_circuit_last_error(void) { return g_cerr.c_str(); }
+
+extern "C" int hq_runtime_init(void) {
+    static bool done = false;
+    if (!done) { MyGlobalVars::init(); done = true; }
+    return HQ_OK;
+}
+
+extern "C" int hq_runtime_init_host_only(int world_size, int rank) {
+    MyGlobalVars::initForTest(world_size, rank);
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_create(int num_qubits, hq_circuit** out) {
+    if (!out || num_qubits < 1 || num_qubits > 40) { g_cerr = "bad qubit count"; return HQ_ERR_ARG; }
+    *out = new hq_circuit{std::unique_ptr<Circuit>(new Circuit(num_qubits)), ""};
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_from_qasm(const char* text, hq_circuit** out) {
+    if (!text || !out) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    std::string err;
+    auto c = hyquas::parseQasmText(text, err);
+    if (!c) { g_cerr = err; return HQ_ERR_ARG; }
+    *out = new hq_circuit{std::move(c), ""};
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_add_gate(hq_circuit* h, int type, int control2, int control, int target, const double* params, int nparams) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    auto P = [&](int i) { return i < nparams && params ? params[i] : 0.0; };
+    const int n = h->c->numQubits;
+    for (int q : {control2, control}) if (q < -1 || q >= n) { g_cerr = "control out of range"; return HQ_ERR_ARG; }
+    if (target < 0 || target >= n) { g_cerr = "target out of range"; return HQ_ERR_ARG; }
+    Gate g;
+    switch ((GateType)type) {
+        case GateType::CCX: g = Gate::CCX(control, control2, target); break;
+        case GateType::CNOT: g = Gate::CNOT(control, target); break;
+        case GateType::CY: g = Gate::CY(control, target); break;
+        case GateType::CZ: g = Gate::CZ(control, target); break;
+        case GateType::CRX: g = Gate::CRX(control, target, P(0)); break;
+        case GateType::CRY: g = Gate::CRY(control, target, P(0)); break;
+        case GateType::CU1: g = Gate::CU1(control, target, P(0)); break;
+        case GateType::CRZ: g = Gate::CRZ(control, target, P(0)); break;
+        case GateType::U1: g = Gate::U1(target, P(0)); break;
+        case GateType::U2: g = Gate::U2(target, P(0), P(1)); break;
+        case GateType::U3: g = Gate::U3(target, P(0), P(1), P(2)); break;
+        case GateType::H: g = Gate::H(target); break;
+        case GateType::X: g = Gate::X(target); break;
+        case GateType::Y: g = Gate::Y(target); break;
+        case GateType::Z: g = Gate::Z(target); break;
+        case GateType::S: g = Gate::S(target); break;
+        case GateType::SDG: g = Gate::SDG(target); break;
+        case GateType::T: g = Gate::T(target); break;
+        case GateType::TDG: g = Gate::TDG(target); break;
+        case GateType::RX: g = Gate::RX(target, P(0)); break;
+        case GateType::RY: g = Gate::RY(target, P(0)); break;
+        case GateType::RZ: g = Gate::RZ(target, P(0)); break;
+        default: g_cerr = "unsupported gate type"; return HQ_ERR_ARG;
+    }
+    h->c->addGate(g);
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_num_qubits(const hq_circuit* h) { return h ? h->c->numQubits : -1; }
+extern "C" int hq_circuit_num_gates(const hq_circuit* h) { return h ? (int)h->c->getGates().size() : -1; }
+
+extern "C" int hq_circuit_compile(hq_circuit* h) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    h->c->compile();
+    return HQ_OK;
+}
+
+// host-only: run the partitioner without touching a GPU and report the shape of the schedule
+extern "C" int hq_circuit_plan_only(hq_circuit* h, int* stages, int* groups, int* swapped_bits) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    Compiler compiler(h->c->numQubits, h->c->getGates());
+    Schedule s = compiler.run();
+    if (stages) *stages = (int)s.localGroups.size();
+    if (groups) *groups = s.numGroups();
+    if (swapped_bits) { *swapped_bits = 0; for (auto& lg : s.localGroups) *swapped_bits += (int)lg.swap.localBit.size(); }
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_run(hq_circuit* h, int copy_back, int destroy, int* time_us, double* device_ms) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    const int us = h->c->run(copy_back != 0, destroy != 0);
+    if (time_us) *time_us = us;
+    if (device_ms) *device_ms = h->c->lastDeviceMs;
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_schedule_info(const hq_circuit* h, int* stages, int* groups, int* gates_in_groups) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    const Schedule& s = h->c->getSchedule();
+    if (stages) *stages = (int)s.localGroups.size();
+    if (groups) *groups = s.numGroups();
+    if (gates_in_groups) {
+        int g = 0;
+        for (auto& lg : s.localGroups) {
+            for (auto& gg : lg.fullGroups) g += (int)gg.gates.size();
+            for (auto& gg : lg.overlapGroups) g += (int)gg.gates.size();
+        }
+        *gates_in_groups = g;
+    }
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_dump(hq_circuit* h, char* buf, size_t cap, size_t* needed) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    h->dump = h->c->stateDump();
+    if (needed) *needed = h->dump.size() + 1;
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, h->dump.size());
+        memcpy(buf, h->dump.data(), n);
+        buf[n] = 0;
+    }
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_amplitudes(hq_circuit* h, double* out_re_im) {
+    if (!h || !out_re_im) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    std::vector<qComplex> st;
+    if (!h->c->fullState(st)) { g_cerr = "full state not available (run with destroy=0 or copy_back=1, single GPU, n<=30)"; return HQ_ERR_UNSUPPORTED; }
+    memcpy(out_re_im, st.data(), st.size() * sizeof(qComplex));
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_logger_flush(char* buf, size_t cap) {
+    std::string all;
+    for (const auto& s : Logger::pending()) all += "Logger: " + s + "\n";
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, all.size());
+        memcpy(buf, all.data(), n);
+        buf[n] = 0;
+    }
+    Logger::print();   // clears; also echoes to stdout like the CLI
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_destroy(hq_circuit* h) {
+    delete h;
+    return HQ_OK;
+}
+
+// ---- TEST HOOK (CPU test-suite only; never used by run()) ---------------------------------------------------
+// Replays the compiled schedule of a single-process circuit on a host array by interpreting each group's device
+// plan with the plan emulator (device/plan_emulator.cpp).  Validates partitioner + lowering + round planner
+// without a GPU; the product path launches the CUDA kernels instead.
+extern "C" int hq_debug_group_plan_emulate(const hq_group_plan* plan, double* state_re_im);
+extern "C" int hq_debug_circuit_emulate(hq_circuit* h, double* state_re_im) {
+    if (!h || !state_re_im) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    if (MyGlobalVars::numGPUs != 1) { g_cerr = "emulation hook is single-process"; return HQ_ERR_UNSUPPORTED; }
+    for (const auto& lg : h->c->getSchedule().localGroups)
+        for (const auto& gg : lg.fullGroups) {
+            int rc = hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(0)), state_re_im);
+            if (rc != HQ_OK) return rc;
+        }
+    return HQ_OK;
+}

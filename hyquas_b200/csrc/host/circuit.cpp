@@ -1,0 +1,193 @@
+#include "circuit.h"
+
+#include <algorithm>
+#include <cassert>
+#include <chrono>
+
+#include "compiler.h"
+#include "executor.h"
+#include "logger.h"
+#include "swap.h"
+using namespace std;
+
+std::string ResultItem::str() const {   // "%lld %.12f: %.12f %.12f\n" = idx |amp|^2 : re im (reference circuit.h:14-16)
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%lld %.12f: %.12f %.12f\n", idx, amp.x * amp.x + amp.y * amp.y, zero_wrapper(amp.x), zero_wrapper(amp.y));
+    return buf;
+}
+
+Circuit::~Circuit() {
+    Executor::release(schedule);
+    destroyState();
+}
+
+void Circuit::destroyState() {
+    for (auto* p : deviceStateVec) hq_state_free(p);
+    deviceStateVec.clear();
+}
+
+void Circuit::compile() {
+    auto t0 = chrono::system_clock::now();
+    Logger::add("Total Gates %d", int(gates.size()));
+    Executor::release(schedule);
+    Compiler compiler(numQubits, gates);
+    schedule = compiler.run();
+    int fullGroups = 0, fullGates = 0, overlapGates = 0;
+    for (auto& lg : schedule.localGroups) {
+        fullGroups += (int)lg.fullGroups.size();
+        for (auto& gg : lg.fullGroups) fullGates += (int)gg.gates.size();
+        for (auto& gg : lg.overlapGroups) overlapGates += (int)gg.gates.size();
+    }
+    Logger::add("Total Groups: %d %d %d %d", int(schedule.localGroups.size()), fullGroups, fullGates, overlapGates);
+    if (getenv("HQ_SHOW_SCHEDULE")) schedule.dump(numQubits);
+    auto t1 = chrono::system_clock::now();
+    Executor::prepare(schedule, numQubits);
+    auto t2 = chrono::system_clock::now();
+    const int d1 = (int)chrono::duration_cast<chrono::microseconds>(t1 - t0).count();
+    const int d2 = (int)chrono::duration_cast<chrono::microseconds>(t2 - t1).count();
+    Logger::add("Compile Time: %d us + %d us = %d us", d1, d2, d1 + d2);
+    compiled = true;
+}
+
+int Circuit::run(bool copy_back, bool destroy) {
+    if (!compiled) compile();
+    const int L = numQubits - MyGlobalVars::bit;
+    destroyState();
+    deviceStateVec.resize(1);
+    void* st = nullptr;
+    checkHq(hq_state_alloc(L, &st));
+    deviceStateVec[0] = static_cast<qComplex*>(st);
+    checkHq(hq_state_init(st, L, MyMPI::rank == 0));
+    checkHq(hq_sync());
+
+    auto start = chrono::system_clock::now();
+    checkHq(hq_timer_start());
+    Executor(deviceStateVec, numQubits, schedule).run();
+    auto end = chrono::system_clock::now();
+    float ms = 0;
+    checkHq(hq_timer_stop_ms(&ms));
+    lastDeviceMs = ms;
+    auto duration = chrono::duration_cast<chrono::microseconds>(end - start);
+    Logger::add("Time Cost: %d us", int(duration.count()));
+
+    collectDump();
+    result.clear();
+    if (copy_back) {
+        const qindex maxAmps = qindex(1) << 29;   // 8 GiB of host memory; larger states stay on the device
+        if ((qindex(1) << L) <= maxAmps) {
+            result.resize(qindex(1) << L);
+            checkHq(hq_state_download(st, L, 0, qindex(1) << L, reinterpret_cast<double*>(result.data())));
+        } else {
+            Logger::add("copy_back skipped: %d local qubits do not fit the host copy budget", L);
+        }
+    }
+    if (destroy) destroyState();
+    return (int)duration.count();
+}
+
+void Circuit::dumpGates() {
+    printf("total Gates: %d\n", (int)gates.size());
+    for (const Gate& g : gates) {
+        for (int i = 0; i < numQubits; i++) {
+            if (i == g.controlQubit || i == g.controlQubit2) printf(".  ");
+            else if (i == g.targetQubit) printf("%-3s", g.name.c_str());
+            else printf("|  ");
+        }
+        printf("\n");
+    }
+}
+
+qindex Circuit::toPhysicalID(qindex idx) {
+    const auto& pos = schedule.finalState.pos;
+    qindex id = 0;
+    for (int i = 0; i < numQubits; i++) if (idx >> i & 1) id |= qindex(1) << pos[i];
+    return id;
+}
+
+qindex Circuit::toLogicID(qindex idx) {
+    const auto& pos = schedule.finalState.pos;
+    qindex id = 0;
+    for (int i = 0; i < numQubits; i++) if (idx >> pos[i] & 1) id |= qindex(1) << i;
+    return id;
+}
+
+qComplex Circuit::ampAtGPU(qindex idx) {
+    const int L = numQubits - MyGlobalVars::bit;
+    const qindex id = toPhysicalID(idx);
+    qComplex ret = make_qComplex(0.0, 0.0);
+    const int owner = (int)(id >> L);
+    if (owner == MyMPI::rank) {
+        assert(!deviceStateVec.empty());
+        checkHq(hq_amp_fetch(deviceStateVec[0], id & ((qindex(1) << L) - 1), reinterpret_cast<double*>(&ret)));
+    }
+    if (MyGlobalVars::numGPUs > 1) hyquas::bcastAmp(&ret, owner);
+    return ret;
+}
+
+ResultItem Circuit::ampAt(qindex idx) {
+    const int L = numQubits - MyGlobalVars::bit;
+    const qindex id = toPhysicalID(idx);
+    if (!result.empty() && (id >> L) == MyMPI::rank) return ResultItem(idx, result[id & ((qindex(1) << L) - 1)]);
+    if (idx < 128 && dumpItems.size() >= 128) return dumpItems[idx];
+    return ResultItem(idx, ampAtGPU(idx));
+}
+
+// What printState shows (reference circuit.cpp:284-309): logical amplitudes 0..127, then every amplitude with
+// |a|^2 > 0.001 and logical index >= 128, ascending.  Captured on the device while the state is alive so that
+// nothing of size 2^n ever has to reach the host.
+void Circuit::collectDump() {
+    const int L = numQubits - MyGlobalVars::bit;
+    const qindex localMask = (qindex(1) << L) - 1;
+    dumpItems.clear();
+    std::vector<ResultItem> mine;
+    const int head = (int)std::min<qindex>(128, qindex(1) << numQubits);
+    for (int i = 0; i < head; i++) {
+        const qindex id = toPhysicalID(i);
+        if ((id >> L) != MyMPI::rank) continue;
+        qComplex a;
+        checkHq(hq_amp_fetch(deviceStateVec[0], id & localMask, reinterpret_cast<double*>(&a)));
+        mine.push_back(ResultItem(i, a));
+    }
+    const int64_t cap = 1024;   // at most 1/0.001 amplitudes can exceed the threshold
+    std::vector<int64_t> idx(cap);
+    std::vector<double> amp(2 * cap);
+    int64_t found = 0;
+    checkHq(hq_dump_scan(deviceStateVec[0], L, 0.001, idx.data(), amp.data(), cap, &found));
+    assert(found <= cap);
+    for (int64_t i = 0; i < found; i++) {
+        const qindex logic = toLogicID(idx[i] | (qindex(MyMPI::rank) << L));
+        if (logic >= 128) mine.push_back(ResultItem(logic, make_qComplex(amp[2 * i], amp[2 * i + 1])));
+    }
+    if (MyGlobalVars::numGPUs > 1) hyquas::gatherItems(mine);   // rank 0 receives everybody's items
+    std::sort(mine.begin(), mine.end());
+    dumpItems.swap(mine);
+}
+
+std::string Circuit::stateDump() {
+    std::string out;
+    for (const auto& item : dumpItems) out += item.str();
+    return out;
+}
+
+void Circuit::printState() {
+    if (MyMPI::rank != 0) return;
+    fputs(stateDump().c_str(), stdout);
+    fflush(stdout);
+}
+
+bool Circuit::fullState(std::vector<qComplex>& out) {
+    if (MyGlobalVars::numGPUs != 1 || numQubits > 30) return false;
+    const qindex N = qindex(1) << numQubits;
+    std::vector<qComplex> phys;
+    if (!result.empty()) phys = result;
+    else if (!deviceStateVec.empty()) {
+        phys.resize(N);
+        checkHq(hq_state_download(deviceStateVec[0], numQubits, 0, N, reinterpret_cast<double*>(phys.data())));
+    } else return false;
+    bool identity = true;
+    for (int i = 0; i < numQubits; i++) identity &= schedule.finalState.pos[i] == i;
+    if (identity) { out.swap(phys); return true; }
+    out.resize(N);
+    for (qindex i = 0; i < N; i++) out[i] = phys[toPhysicalID(i)];
+    return true;
+}

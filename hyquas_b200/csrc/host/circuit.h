@@ -1,0 +1,53 @@
+// User-facing circuit object: the same surface as the reference's Circuit / ResultItem (src/circuit.h:9-47):
+//   Circuit c(n); c.addGate(Gate::H(0)); c.compile(); int us = c.run(); c.printState();
+// run() returns the elapsed microseconds of the execution phase ("Time Cost", src/circuit.cpp:22,46-52).
+#pragma once
+
+#include <string>
+#include <vector>
+#include "utils.h"
+#include "gate.h"
+#include "schedule.h"
+
+struct ResultItem {
+    ResultItem() = default;
+    ResultItem(const qindex& idx, const qComplex& amp): idx(idx), amp(amp) {}
+    qindex idx;
+    qComplex amp;
+    std::string str() const;
+    void print() { fputs(str().c_str(), stdout); }
+    bool operator < (const ResultItem& b) const { return idx < b.idx; }
+};
+
+class Circuit {
+public:
+    Circuit(int numQubits): numQubits(numQubits) {}
+    ~Circuit();
+    void compile();
+    int run(bool copy_back = true, bool destroy = true);
+    void addGate(const Gate& gate) { gates.push_back(gate); }
+    void dumpGates();
+    void printState();
+    ResultItem ampAt(qindex idx);
+    qComplex ampAtGPU(qindex idx);
+    const int numQubits;
+
+    // extras used by the C-ABI / tests / bench
+    std::string stateDump();                          // the text printState() prints
+    const Schedule& getSchedule() const { return schedule; }
+    const std::vector<Gate>& getGates() const { return gates; }
+    bool fullState(std::vector<qComplex>& out);       // all 2^n amplitudes in LOGICAL order (single process, small n)
+    double lastDeviceMs = 0;                          // CUDA-event time of the last run()
+    void destroyState();
+
+private:
+    qindex toPhysicalID(qindex idx);
+    qindex toLogicID(qindex idx);
+    void collectDump();
+    std::vector<Gate> gates;
+    std::vector<qComplex*> deviceStateVec;
+    Schedule schedule;
+    std::vector<qComplex> result;                     // host copy in PHYSICAL order (copy_back)
+    std::vector<ResultItem> dumpItems;                // what printState() shows, captured before destroy
+    bool compiled = false;
+};

@@ -1,0 +1,193 @@
+#include "compiler.h"
+
+#include <algorithm>
+#include <cassert>
+
+#include "evaluator.h"
+#include "logger.h"
+
+namespace hyquas {
+
+// A gate acts "non-diagonally" on its target unless its matrix is diagonal, and "diagonally" on its controls.
+// Two gates commute when every qubit they share is acted on diagonally by both.  A skipped gate therefore
+// blocks (a) everything on its non-diagonal qubit, (b) non-diagonal action on its diagonal qubits.
+std::vector<int> runnableGates(const std::vector<Gate>& gates, const std::vector<int>& order, qindex tileSet, int cap) {
+    std::vector<int> out;
+    qindex blockedAll = 0, blockedNonDiag = 0;
+    int seen = 0;
+    for (int gi : order) {
+        if (++seen > cap) break;
+        const Gate& g = gates[gi];
+        const bool diag = g.isDiagonal();
+        qindex qn = 0, qd = 0;
+        (diag ? qd : qn) |= qindex(1) << g.targetQubit;
+        if (g.controlQubit >= 0) qd |= qindex(1) << g.controlQubit;
+        if (g.controlQubit2 >= 0) qd |= qindex(1) << g.controlQubit2;
+        bool ok = !(qn & (blockedAll | blockedNonDiag)) && !(qd & blockedAll);
+        if (ok && !diag && !(tileSet >> g.targetQubit & 1)) ok = false;
+        if (ok) out.push_back(gi);
+        else { blockedAll |= qn; blockedNonDiag |= qd; }
+    }
+    return out;
+}
+
+// Move to a layout in which exactly `newLocals` are local.  Outgoing qubits are first brought to the top
+// local positions (in-place bit swaps), then traded with the global positions of the incoming qubits.
+SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal) {
+    SwapPlan plan;
+    std::vector<int> outgoing, incoming;
+    for (int p = 0; p < numLocal; p++) if (!(newLocals >> state.layout[p] & 1)) outgoing.push_back(state.layout[p]);
+    for (int p = numLocal; p < numQubits; p++) if (newLocals >> state.layout[p] & 1) incoming.push_back(state.layout[p]);
+    assert(outgoing.size() == incoming.size());
+    const int k = (int)outgoing.size();
+    // outgoing qubits that already sit in the top-k window keep their place
+    std::vector<int> slots;
+    for (int p = numLocal - k; p < numLocal; p++) slots.push_back(p);
+    std::vector<int> movers;
+    for (int q : outgoing) {
+        auto it = std::find(slots.begin(), slots.end(), state.pos[q]);
+        if (it != slots.end()) slots.erase(it); else movers.push_back(q);
+    }
+    for (size_t i = 0; i < movers.size(); i++) {
+        const int a = state.pos[movers[i]], b = slots[i];
+        plan.localPerm.push_back({a, b});
+        state.swapPhysical(a, b);
+    }
+    std::sort(incoming.begin(), incoming.end(), [&](int x, int y) { return state.pos[x] < state.pos[y]; });
+    for (int i = 0; i < k; i++) {
+        const int lb = numLocal - k + i, gb = state.pos[incoming[i]];
+        plan.localBit.push_back(lb);
+        plan.globalBit.push_back(gb - numLocal);
+        state.swapPhysical(lb, gb);
+    }
+    return plan;
+}
+
+}  // namespace hyquas
+
+Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
+    : numQubits(numQubits_), numLocal(numQubits_ - MyGlobalVars::bit), gates(std::move(inputGates)) {
+    tileBits = std::min(hq_group_tile_bits(), numLocal);
+    pinnedBits = std::min(5, tileBits);
+    if (const char* e = getenv("HQ_PINNED_BITS")) pinnedBits = std::max(hq_group_min_run_bits(), std::min(atoi(e), tileBits));
+    maxGroupGates = 384;
+    if (const char* e = getenv("HQ_MAX_GROUP_GATES")) maxGroupGates = std::max(1, atoi(e));
+}
+
+// ---- stage split --------------------------------------------------------------------------------------
+std::vector<Compiler::Stage> Compiler::splitStages() const {
+    std::vector<Stage> stages;
+    if (MyGlobalVars::bit == 0) {
+        stages.push_back({gates, (qindex(1) << numQubits) - 1});
+        return stages;
+    }
+    std::vector<int> remaining(gates.size());
+    for (size_t i = 0; i < gates.size(); i++) remaining[i] = (int)i;
+    qindex prevLocals = (qindex(1) << numLocal) - 1;
+    while (!remaining.empty()) {
+        // grow the local set greedily: repeatedly add the qubit that unlocks the most gates
+        qindex locals = 0;
+        while (bitCount(locals) < numLocal) {
+            const size_t base = hyquas::runnableGates(gates, remaining, locals, 4096).size();
+            int best = -1; size_t bestGain = base;
+            for (int q = 0; q < numQubits; q++) {
+                if (locals >> q & 1) continue;
+                const size_t gain = hyquas::runnableGates(gates, remaining, locals | qindex(1) << q, 4096).size();
+                // ties prefer qubits that are already local (fewer bits to swap)
+                if (gain > bestGain || (gain == bestGain && best >= 0 && gain > base && (prevLocals >> q & 1) && !(prevLocals >> best & 1))) {
+                    best = q; bestGain = gain;
+                }
+            }
+            if (best < 0) break;
+            locals |= qindex(1) << best;
+        }
+        // pad with currently-local qubits first, then anything
+        for (int pass = 0; pass < 2 && bitCount(locals) < numLocal; pass++)
+            for (int q = 0; q < numQubits && bitCount(locals) < numLocal; q++)
+                if (!(locals >> q & 1) && (pass == 1 || (prevLocals >> q & 1))) locals |= qindex(1) << q;
+        std::vector<int> take = hyquas::runnableGates(gates, remaining, locals, 1 << 30);
+        assert(!take.empty());
+        Stage st; st.locals = locals;
+        for (int gi : take) st.gates.push_back(gates[gi]);
+        std::vector<int> rest;
+        std::set_difference(remaining.begin(), remaining.end(), take.begin(), take.end(), std::back_inserter(rest));
+        remaining.swap(rest);
+        stages.push_back(std::move(st));
+        prevLocals = locals;
+    }
+    if (stages.empty()) stages.push_back({{}, (qindex(1) << numLocal) - 1});
+    return stages;
+}
+
+// ---- gate groups inside one stage ----------------------------------------------------------------------
+std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal) const {
+    std::vector<GateGroup> groups;
+    std::vector<int> remaining(stageGates.size());
+    for (size_t i = 0; i < stageGates.size(); i++) remaining[i] = (int)i;
+    const int K = std::min(tileBits, nLocal), C = std::min(pinnedBits, K);
+    qindex localSet = 0;
+    for (int p = 0; p < nLocal; p++) localSet |= qindex(1) << state.layout[p];
+    const int lookahead = 2048;
+    while (!remaining.empty()) {
+        qindex tile = 0;
+        for (int p = 0; p < C; p++) tile |= qindex(1) << state.layout[p];
+        size_t cur = hyquas::runnableGates(stageGates, remaining, tile, lookahead).size();
+        while (bitCount(tile) < K) {
+            int best = -1; size_t bestGain = cur;
+            for (int p = C; p < nLocal; p++) {
+                const int q = state.layout[p];
+                if (tile >> q & 1) continue;
+                const size_t gain = hyquas::runnableGates(stageGates, remaining, tile | qindex(1) << q, lookahead).size();
+                if (gain > bestGain) { best = q; bestGain = gain; }
+            }
+            if (best < 0) break;
+            tile |= qindex(1) << best;
+            cur = bestGain;
+        }
+        for (int p = 0; p < nLocal && bitCount(tile) < K; p++)   // pad with the lowest free physical bits (longer runs)
+            if (!(tile >> state.layout[p] & 1)) tile |= qindex(1) << state.layout[p];
+        std::vector<int> take = hyquas::runnableGates(stageGates, remaining, tile, lookahead);
+        if ((int)take.size() > maxGroupGates) take.resize(maxGroupGates);   // a prefix of a runnable set is runnable
+        assert(!take.empty());
+        GateGroup gg;
+        gg.backend = Backend::PerGate;
+        gg.relatedQubits = tile;
+        gg.state = state;
+        for (int gi : take) gg.gates.push_back(stageGates[gi]);
+        std::vector<GateType> tys;
+        for (const Gate& g : gg.gates) tys.push_back(g.type);
+        gg.predictedMs = Evaluator::getInstance()->perfPerGate(nLocal, tys);
+        std::vector<int> rest;
+        std::set_difference(remaining.begin(), remaining.end(), take.begin(), take.end(), std::back_inserter(rest));
+        remaining.swap(rest);
+        groups.push_back(std::move(gg));
+    }
+    return groups;
+}
+
+Schedule Compiler::run() {
+    Schedule schedule;
+    State state(numQubits);
+    std::vector<Stage> stages = splitStages();
+    for (size_t s = 0; s < stages.size(); s++) {
+        LocalGroup lg;
+        lg.relatedQubits = stages[s].locals;
+        if (s == 0) {
+            // |0...0> is invariant under qubit relabelling: just declare the stage-0 locals to be at [0, numLocal)
+            State st(numQubits);
+            int lo = 0, hi = numLocal;
+            for (int q = 0; q < numQubits; q++) {
+                const int p = (stages[s].locals >> q & 1) ? lo++ : hi++;
+                st.pos[q] = p; st.layout[p] = q;
+            }
+            state = st;
+        } else {
+            lg.swap = hyquas::planSwap(state, stages[s].locals, numQubits, numLocal);
+        }
+        lg.state = state;
+        lg.fullGroups = cutGroups(stages[s].gates, state, numLocal);
+        schedule.localGroups.push_back(std::move(lg));
+    }
+    schedule.finalState = state;
+    return schedule;
+}

@@ -1,0 +1,40 @@
+// Hybrid partitioner: gate list -> Schedule.
+//   1. split the circuit into communication stages (each stage's non-diagonal targets fit in the local qubits),
+//   2. plan the global<->local swap between consecutive stages,
+//   3. cut each stage into gate groups (one kernel launch = one sweep each) and pick the backend per group
+//      from the evaluator's measured cost model.
+// Plays the role of the reference's Compiler / SimpleCompiler / AdvanceCompiler (src/compiler.h:9-61,
+// src/compiler.cpp:70-452); the algorithms are new (frontier scans with commutation-aware blocking and a
+// greedy qubit-gain search instead of the std::bitset reachability DP).
+#pragma once
+#include <vector>
+
+#include "gate.h"
+#include "schedule.h"
+#include "utils.h"
+
+class Compiler {
+public:
+    Compiler(int numQubits, std::vector<Gate> inputGates);
+    Schedule run();
+
+    // knobs (defaults come from the device layer / environment)
+    int tileBits;      // qubits per tile of the gate-group kernel
+    int pinnedBits;    // lowest physical bits always kept in the tile (contiguous-run length of HBM accesses)
+    int maxGroupGates; // cap on gates per group
+private:
+    struct Stage { std::vector<Gate> gates; qindex locals; };
+    std::vector<Stage> splitStages() const;
+    std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal) const;
+    int numQubits;
+    int numLocal;
+    std::vector<Gate> gates;
+};
+
+namespace hyquas {
+// Frontier scan shared by the stage splitter, the group cutter and (on the device side) the round builder:
+// which of `gates` (indices into it, in program order) can run now if exactly the qubits in `tileSet` may be
+// non-diagonal targets?  Gates that cannot run block later gates they do not commute with.
+std::vector<int> runnableGates(const std::vector<Gate>& gates, const std::vector<int>& order, qindex tileSet, int cap);
+hyquas::SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal);
+}

@@ -1,0 +1,34 @@
+// Time predictor used by the partitioner to price a gate group on this GPU.
+// Same role and entry points as the reference's Evaluator singleton (src/evaluator.h:16-149,
+// src/evaluator.cpp:111-229) but the model is a roofline: a group costs
+//     max( sweep time of the local state at measured HBM bandwidth,  sum of per-gate in-register cost )
+// with per-gate-class costs calibrated by the B200 microbenchmarks (tools/calibrate.py writes the parameter
+// file; built-in defaults are the values measured on this pool's B200).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "gate.h"
+#include "schedule.h"
+#include "utils.h"
+
+class Evaluator {
+public:
+    static Evaluator* getInstance();
+    // predicted milliseconds for one gate-group launch over 2^numQubits local amplitudes
+    double perfPerGate(int numQubits, const GateGroup* gg);
+    double perfPerGate(int numQubits, const std::vector<GateType>& types);
+    // predicted milliseconds for one fused dense (TransMM) launch with a 2^blasSize x 2^blasSize matrix
+    double perfBLAS(int numQubits, int blasSize);
+    bool PerGateOrBLAS(const GateGroup* gg_pergate, const GateGroup* gg_blas, int numQubits, int blasSize);
+    void loadParam(int numQubits);          // optional override from $HYQUAS_PARAM_FILE
+    // model constants (public so that the calibration tool and tests can read/write them)
+    double hbmGBs;                          // achieved sweep bandwidth of the gate-group kernel (read+write)
+    double gateNs[32];                      // per-gate cost per 2^30 amplitudes in ms, indexed by GateType
+    double roundMs30;                       // cost of one extra register round per 2^30 amplitudes, ms
+    double denseMs30[8];                    // fused dense kernel, per 2^30 amplitudes, indexed by matrix qubits
+    double launchMs;                        // fixed per-launch overhead
+private:
+    Evaluator();
+    bool loaded = false;
+};

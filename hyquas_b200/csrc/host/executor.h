@@ -1,0 +1,29 @@
+// Schedule interpreter for one process / one GPU.
+//   prepare(): lowers every gate group for THIS shard of the state (global controls resolved, diagonal gates on
+//              global qubits folded into phases) and builds the device plans -- done once, at compile time;
+//   run():     issues the launches: [swap + per-chunk overlap groups] then full groups, stage by stage.
+// Role of the reference's Executor (src/executor.h:10-54, src/executor.cpp:33-57,190-403,462-575) minus
+// everything its kernels needed from the host per launch (threadBias tables, constant-memory uploads,
+// cuTT/cuBLAS calls).
+#pragma once
+#include <vector>
+
+#include "schedule.h"
+#include "utils.h"
+
+class Executor {
+public:
+    Executor(std::vector<qComplex*> deviceStateVec, int numQubits, Schedule& schedule);
+    void run();
+    static void prepare(Schedule& schedule, int numQubits);   // build device plans (idempotent)
+    static void release(Schedule& schedule);                  // destroy device plans
+    // Lower one logical gate for the sub-state whose physical index bits >= numLocal equal `highIndex`.
+    // Returns false when the gate acts as identity there.
+    static bool lowerGate(const Gate& gate, const State& state, int numLocal, qindex highIndex, hq_gate& out);
+private:
+    void applyGateGroup(GateGroup& gg, int chunk);
+    void finalize();
+    std::vector<qComplex*> deviceStateVec;
+    int numQubits;
+    Schedule& schedule;
+};

@@ -1,0 +1,94 @@
+/*
+ * hyquas_b200.h -- C-ABI of libhyquas_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and POD structs only, every entry point
+ * returns an int status (0 = HQ_OK).  Each block below names the reference interface it stands in
+ * for (paths relative to the HyQuas tree).  The reference's public C++ surface (Circuit / Gate /
+ * MyGlobalVars / Logger, src/circuit.h, src/gate.h, src/utils.h, src/logger.h) is re-implemented on top of
+ * this layer in hyquas_b200/csrc/host/ with the same names, so main.cpp and the micro-benchmark drivers of the
+ * reference compile unchanged against it; see INTEGRATION.md.
+ */
+#ifndef HYQUAS_B200_H
+#define HYQUAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HQ_OK 0
+#define HQ_ERR_CUDA 1       /* a CUDA runtime call failed; message via hq_last_error() */
+#define HQ_ERR_ARG 2        /* invalid argument (bad mask, target outside the tile, ...) */
+#define HQ_ERR_UNSUPPORTED 3
+#define HQ_ERR_NCCL 4
+
+/* Gate type numbering == enum class GateType of the reference (src/gate.h:7-9); the evaluator
+ * preprocess tool iterates these by integer value (evaluator-preprocess/process.cpp:26,55). */
+enum hq_gate_type {
+    HQ_CCX = 0, HQ_CNOT, HQ_CY, HQ_CZ, HQ_CRX, HQ_CRY, HQ_CU1, HQ_CRZ, HQ_U1, HQ_U2, HQ_U3, HQ_H, HQ_X, HQ_Y, HQ_Z,
+    HQ_S, HQ_SDG, HQ_T, HQ_TDG, HQ_RX, HQ_RY, HQ_RZ, HQ_TOTAL, HQ_ID, HQ_GII, HQ_GZZ, HQ_GOC, HQ_GCC
+};
+
+/* One lowered gate of a group, addressed by PHYSICAL LOCAL bit positions of the amplitude index
+ * (0 .. L-1).  Replaces KernelGate (src/gate.h:68-110): there, operands are shared-memory bit
+ * indices or block-index bit indices plus an *IsGlobal flag; here the kernel derives that itself
+ * from tile_mask.  target == -1 means "no target" (a scalar applied to every amplitude: GII/GZZ/GCC
+ * produced when a diagonal gate sits on a global qubit, src/executor.cpp:286-398).
+ * mat is row-major {m00, m01, m10, m11} x {re, im}, i.e. KernelGate's r00,i00,...,r11,i11. */
+typedef struct hq_gate {
+    int32_t type;      /* enum hq_gate_type; only used to pick specialised arithmetic, mat is authoritative */
+    int32_t target;    /* physical local bit, or -1 */
+    int32_t control;   /* physical local bit, or -1 */
+    int32_t control2;  /* physical local bit, or -1 */
+    double  mat[8];
+} hq_gate;
+
+const char* hq_last_error(void);
+const char* hq_version(void);
+
+/* ---- runtime (replaces MyGlobalVars::init, src/utils.cpp:17-60) ------------------------------- */
+int hq_device_count(int* n);
+int hq_init(int device);                       /* bind this process to one GPU; creates the compute + comm streams */
+int hq_shutdown(void);
+int hq_sync(void);                             /* Executor::finalize's cudaStreamSynchronize, src/executor.cpp:634-640 */
+int hq_device_info(char* name, size_t cap, int* sm_count, size_t* total_mem);
+
+/* ---- state vector (replaces kernelInit / kernelDeviceToHost / kernelGetAmp / kernelDestroy,
+ *      src/kernelSimple.cu:9-37,518-530).  One allocation of 16 * 2^L bytes: every kernel here is
+ *      in place, so the reference's doubled buffer (kernelSimple.cu:10-13) does not exist. ------- */
+int hq_state_alloc(int L, void** state);
+int hq_state_free(void* state);
+int hq_state_init(void* state, int L, int set_amp0);          /* zero; amp[0] = 1 if set_amp0 (rank holding |0..0>) */
+int hq_state_download(const void* state, int L, int64_t first, int64_t count, double* host_re_im);
+int hq_state_upload(void* state, int L, int64_t first, int64_t count, const double* host_re_im);
+int hq_amp_fetch(const void* state, int64_t idx, double out_re_im[2]);
+/* On-device threshold scan used by printState (src/circuit.cpp:299-309) so that 32+ qubit states
+ * never travel to the host: returns physical local indices (ascending) with |a|^2 > thresh. */
+int hq_dump_scan(const void* state, int L, double thresh, int64_t* idx_out, double* amp_out, int64_t cap, int64_t* found);
+int hq_state_norm2(const void* state, int L, double* out);
+
+/* ---- gate-group kernel (replaces copyGatesToSymbol + launchExecutor, src/kernel.h:25-28,
+ *      src/kernelOpt.cu:425-433,499-506, and the mask bookkeeping of Executor::prepareBitMap /
+ *      getLogicShareMap, src/executor.cpp:598-632).
+ *      tile_mask selects the physical bits that vary inside one tile (popcount = hq_group_tile_bits(),
+ *      low hq_group_min_run_bits() bits must be set); every non-diagonal target must lie in the tile;
+ *      controls and diagonal targets may be anywhere in [0, L).  state is updated in place. ---------- */
+typedef struct hq_group_plan hq_group_plan;
+int hq_group_tile_bits(void);
+int hq_group_min_run_bits(void);
+int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* gates, int ngates, hq_group_plan** plan);
+int hq_group_plan_launch(const hq_group_plan* plan, void* state, int on_comm_stream);
+int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* ops, int* grid, int* smem_bytes);
+int hq_group_plan_destroy(hq_group_plan* plan);
+int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
+
+/* ---- timing helpers (cudaEvent pairs on the compute stream; MEASURE_STAGE, src/executor.cpp:406-458) */
+int hq_timer_start(void);
+int hq_timer_stop_ms(float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYQUAS_B200_H */
