@@ -54,6 +54,7 @@ _SIGS = {
     "hq_group_plan_create": (_c.c_int, [_c.c_int, _c.c_uint64, _P(HqGate), _c.c_int, _P(_c.c_void_p)]),
     "hq_group_plan_launch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int]),
     "hq_group_plan_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_group_plan_table_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
     "hq_timer_start": (_c.c_int, []),
@@ -70,6 +71,10 @@ _SIGS = {
     "hq_circuit_compile": (_c.c_int, [_c.c_void_p]),
     "hq_circuit_plan_only": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
     "hq_circuit_run": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_double)]),
+    "hq_circuit_prepare_state": (_c.c_int, [_c.c_void_p]),
+    "hq_circuit_execute": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_double), _P(_c.c_float), _c.c_int, _P(_c.c_int)]),
+    "hq_circuit_norm2": (_c.c_int, [_c.c_void_p, _P(_c.c_double)]),
+    "hq_circuit_io_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_size_t), _P(_c.c_size_t)]),
     "hq_circuit_schedule_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
     "hq_circuit_dump": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _P(_c.c_size_t)]),
     "hq_circuit_amplitudes": (_c.c_int, [_c.c_void_p, _c.c_void_p]),

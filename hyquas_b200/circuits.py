@@ -250,3 +250,35 @@ def generate(name: str) -> str:
 if __name__ == "__main__":
     import sys
     sys.stdout.write(generate(sys.argv[1]))
+
+
+def inverse(text: str) -> str:
+    """U -> U^dagger in the same dialect (gate order reversed, each gate inverted).  Used for the
+    size-independent round-trip property U^dagger U |0> = |0> at full benchmark sizes."""
+    lines = [l for l in text.split("\n") if l.strip()]
+    head = [l for l in lines if l.split()[0] in ("OPENQASM", "include", "qreg", "//")]
+    body = [l for l in lines if l not in head]
+    self_inv = {"h", "x", "y", "z", "cx", "cy", "cz", "ccx"}
+    swap = {"s": "sdg", "sdg": "s", "t": "tdg", "tdg": "t"}
+    out = []
+    for l in reversed(body):
+        tok, operand = l.split()[0], l.split()[1]
+        name = tok.split("(")[0]
+        if name in self_inv:
+            out.append(l)
+        elif name in swap:
+            out.append(f"{swap[name]} {operand}")
+        else:
+            ps = tok[tok.index("(") + 1: tok.rindex(")")].split(",")
+
+            def neg(p):
+                if p.startswith("pi"):
+                    v = math.pi * float(p[3:]) if p[2] == "*" else math.pi / float(p[3:])
+                    return "%.17g" % (-v)
+                return p[1:] if p.startswith("-") else "-" + p
+            if name == "u3":
+                ps = [neg(ps[0]), neg(ps[2]), neg(ps[1])]
+            else:
+                ps = [neg(p) for p in ps]
+            out.append(f"{name}({','.join(ps)}) {operand}")
+    return "".join(l + "\n" for l in head + out)

@@ -590,6 +590,12 @@ extern "C" int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* o
     return HQ_OK;
 }
 
+extern "C" int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes) {
+    HQ_REQUIRE(plan != nullptr && bytes != nullptr, "null argument");
+    *bytes = (int)plan->blob.size();
+    return HQ_OK;
+}
+
 extern "C" int hq_group_plan_destroy(hq_group_plan* plan) {
     if (!plan) return HQ_OK;
     if (plan->dev_blob) cudaFree(plan->dev_blob);

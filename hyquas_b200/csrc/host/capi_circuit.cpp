@@ -107,6 +107,36 @@ extern "C" int hq_circuit_run(hq_circuit* h, int copy_back, int destroy, int* ti
     return HQ_OK;
 }
 
+extern "C" int hq_circuit_prepare_state(hq_circuit* h) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    h->c->prepareState();
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_execute(hq_circuit* h, int* time_us, double* device_ms, float* per_group_ms, int cap, int* ngroups) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    std::vector<float> per;
+    const int us = h->c->execute(per_group_ms ? &per : nullptr);
+    if (time_us) *time_us = us;
+    if (device_ms) *device_ms = h->c->lastDeviceMs;
+    if (per_group_ms) for (int i = 0; i < cap && i < (int)per.size(); i++) per_group_ms[i] = per[i];
+    if (ngroups) *ngroups = (int)per.size();
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_norm2(hq_circuit* h, double* out) {
+    if (!h || !out) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    *out = h->c->norm2();
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_io_bytes(const hq_circuit* h, size_t* h2d_plan_bytes, size_t* d2h_dump_bytes) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    if (h2d_plan_bytes) *h2d_plan_bytes = h->c->planBytes();
+    if (d2h_dump_bytes) *d2h_dump_bytes = h->c->dumpBytes();
+    return HQ_OK;
+}
+
 extern "C" int hq_circuit_schedule_info(const hq_circuit* h, int* stages, int* groups, int* gates_in_groups) {
     if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
     const Schedule& s = h->c->getSchedule();

@@ -49,26 +49,38 @@ void Circuit::compile() {
     compiled = true;
 }
 
-int Circuit::run(bool copy_back, bool destroy) {
+void Circuit::prepareState() {
     if (!compiled) compile();
     const int L = numQubits - MyGlobalVars::bit;
-    destroyState();
-    deviceStateVec.resize(1);
-    void* st = nullptr;
-    checkHq(hq_state_alloc(L, &st));
-    deviceStateVec[0] = static_cast<qComplex*>(st);
-    checkHq(hq_state_init(st, L, MyMPI::rank == 0));
+    if (deviceStateVec.empty()) {
+        void* st = nullptr;
+        checkHq(hq_state_alloc(L, &st));
+        deviceStateVec.assign(1, static_cast<qComplex*>(st));
+    }
+    checkHq(hq_state_init(deviceStateVec[0], L, MyMPI::rank == 0));
     checkHq(hq_sync());
+}
 
+// Everything the reference times as "Time Cost" (circuit.cpp:22-52 there): issue all launches, final sync.
+int Circuit::execute(std::vector<float>* perGroupMs) {
     auto start = chrono::system_clock::now();
     checkHq(hq_timer_start());
-    Executor(deviceStateVec, numQubits, schedule).run();
+    Executor ex(deviceStateVec, numQubits, schedule);
+    ex.perGroupMs = perGroupMs;
+    ex.run();
     auto end = chrono::system_clock::now();
     float ms = 0;
     checkHq(hq_timer_stop_ms(&ms));
     lastDeviceMs = ms;
-    auto duration = chrono::duration_cast<chrono::microseconds>(end - start);
-    Logger::add("Time Cost: %d us", int(duration.count()));
+    return (int)chrono::duration_cast<chrono::microseconds>(end - start).count();
+}
+
+int Circuit::run(bool copy_back, bool destroy) {
+    destroyState();
+    prepareState();
+    const int L = numQubits - MyGlobalVars::bit;
+    const int us = execute();
+    Logger::add("Time Cost: %d us", us);
 
     collectDump();
     result.clear();
@@ -76,13 +88,32 @@ int Circuit::run(bool copy_back, bool destroy) {
         const qindex maxAmps = qindex(1) << 29;   // 8 GiB of host memory; larger states stay on the device
         if ((qindex(1) << L) <= maxAmps) {
             result.resize(qindex(1) << L);
-            checkHq(hq_state_download(st, L, 0, qindex(1) << L, reinterpret_cast<double*>(result.data())));
+            checkHq(hq_state_download(deviceStateVec[0], L, 0, qindex(1) << L, reinterpret_cast<double*>(result.data())));
         } else {
             Logger::add("copy_back skipped: %d local qubits do not fit the host copy budget", L);
         }
     }
     if (destroy) destroyState();
-    return (int)duration.count();
+    return us;
+}
+
+double Circuit::norm2() {
+    double v = 0;
+    if (!deviceStateVec.empty()) checkHq(hq_state_norm2(deviceStateVec[0], numQubits - MyGlobalVars::bit, &v));
+    return v;
+}
+
+size_t Circuit::planBytes() const {
+    size_t total = 0;
+    for (const auto& lg : schedule.localGroups)
+        for (const auto* groups : {&lg.overlapGroups, &lg.fullGroups})
+            for (const auto& gg : *groups)
+                for (void* p : gg.plans) {
+                    int bytes = 0;
+                    hq_group_plan_table_bytes(static_cast<hq_group_plan*>(p), &bytes);
+                    total += bytes;
+                }
+    return total;
 }
 
 void Circuit::dumpGates() {

@@ -38,6 +38,11 @@ public:
     const std::vector<Gate>& getGates() const { return gates; }
     bool fullState(std::vector<qComplex>& out);       // all 2^n amplitudes in LOGICAL order (single process, small n)
     double lastDeviceMs = 0;                          // CUDA-event time of the last run()
+    void prepareState();                              // (re)allocate + |0..0>
+    int execute(std::vector<float>* perGroupMs = nullptr);   // the timed part of run() on the resident state
+    double norm2();                                   // sum |a|^2 over this process' shard
+    size_t planBytes() const;                         // bytes of device tables uploaded by compile()
+    size_t dumpBytes() const { return dumpItems.size() * sizeof(ResultItem); }
     void destroyState();
 
 private:

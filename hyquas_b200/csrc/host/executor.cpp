@@ -96,6 +96,7 @@ void Executor::release(Schedule& schedule) {
 
 void Executor::applyGateGroup(GateGroup& gg, int chunk) {
     const int L = numQubits - MyGlobalVars::bit;
+    if (perGroupMs) checkHq(hq_timer_start());
     if (chunk < 0) {
         checkHq(hq_group_plan_launch(static_cast<hq_group_plan*>(gg.plans[0]), deviceStateVec[0], 0));
     } else {
@@ -104,6 +105,11 @@ void Executor::applyGateGroup(GateGroup& gg, int chunk) {
         while ((1 << k) < nChunks) k++;
         qComplex* base = deviceStateVec[0] + ((qindex)chunk << (L - k));
         checkHq(hq_group_plan_launch(static_cast<hq_group_plan*>(gg.plans[chunk]), base, 0));
+    }
+    if (perGroupMs) {
+        float ms = 0;
+        checkHq(hq_timer_stop_ms(&ms));
+        perGroupMs->push_back(ms);
     }
 }
 

@@ -81,6 +81,7 @@ int hq_group_min_run_bits(void);
 int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* gates, int ngates, hq_group_plan** plan);
 int hq_group_plan_launch(const hq_group_plan* plan, void* state, int on_comm_stream);
 int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* ops, int* grid, int* smem_bytes);
+int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes);   /* size of the uploaded device tables */
 int hq_group_plan_destroy(hq_group_plan* plan);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 

@@ -31,6 +31,12 @@ int hq_circuit_compile(hq_circuit* c);                       /* Circuit::compile
 int hq_circuit_plan_only(hq_circuit* c, int* stages, int* groups, int* swapped_bits);   /* Compiler::run only (host) */
 /* Circuit::run: returns wall microseconds of the execution phase ("Time Cost") and the CUDA-event time */
 int hq_circuit_run(hq_circuit* c, int copy_back, int destroy, int* time_us, double* device_ms);
+/* run() split in two so that a resident state can be re-used: allocate + |0..0>, then the timed execution phase.
+ * per_group_ms (optional): CUDA-event time of each gate-group launch (MEASURE_STAGE, src/executor.cpp:406-458). */
+int hq_circuit_prepare_state(hq_circuit* c);
+int hq_circuit_execute(hq_circuit* c, int* time_us, double* device_ms, float* per_group_ms, int cap, int* ngroups);
+int hq_circuit_norm2(hq_circuit* c, double* out);
+int hq_circuit_io_bytes(const hq_circuit* c, size_t* h2d_plan_bytes, size_t* d2h_dump_bytes);
 int hq_circuit_schedule_info(const hq_circuit* c, int* stages, int* groups, int* gates_in_groups);
 int hq_circuit_dump(hq_circuit* c, char* buf, size_t cap, size_t* needed);              /* printState text */
 int hq_circuit_amplitudes(hq_circuit* c, double* out_re_im); /* all 2^n amplitudes, logical order (small n) */

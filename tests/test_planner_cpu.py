@@ -1,0 +1,115 @@
+"""Host logic on CPU: partitioner + gate lowering + round planner, checked by interpreting the device tables with the
+plan emulator (a test hook) and comparing with the oracle.  The CUDA kernel itself is covered by the -m gpu tests."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from hyquas_b200 import api, circuits as C
+from hyquas_b200._lib import HqGate, check, lib
+from oracle import oracle as O
+
+lib.hq_debug_circuit_emulate.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+
+
+def pack(gates):
+    arr = (HqGate * max(1, len(gates)))()
+    for i, g in enumerate(gates):
+        arr[i].type, arr[i].target, arr[i].control, arr[i].control2 = 0, g.target, g.control, g.control2
+        m = np.asarray(g.mat).reshape(4)
+        for j in range(4):
+            arr[i].mat[2 * j], arr[i].mat[2 * j + 1] = m[j].real, m[j].imag
+    return arr
+
+
+def random_state(n, seed):
+    r = np.random.default_rng(seed)
+    s = (r.standard_normal(1 << n) + 1j * r.standard_normal(1 << n)).astype(np.complex128)
+    return s / np.linalg.norm(s)
+
+
+@pytest.mark.parametrize("n,K,seed", [(12, 10, 0), (13, 11, 1), (14, 12, 2), (15, 12, 3), (12, 12, 4), (16, 11, 5)])
+def test_group_plan_tables_match_oracle(n, K, seed):
+    rng = random.Random(seed)
+    rest = list(range(3, n))
+    rng.shuffle(rest)
+    tile = [0, 1, 2] + sorted(rest[:K - 3])
+    mask = sum(1 << b for b in tile)
+    _, gates = O.parse_qasm(C.random_circuit(n, 250, seed))
+    keep = [g for g in gates if (g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target in tile]
+    plan = ctypes.c_void_p()
+    check(lib.hq_group_plan_create(n, mask, pack(keep), len(keep), ctypes.byref(plan)))
+    st = random_state(n, seed)
+    want = st.copy()
+    O.apply(want, n, keep)
+    check(lib.hq_debug_group_plan_emulate(plan, st.ctypes.data))
+    lib.hq_group_plan_destroy(plan)
+    assert np.max(np.abs(st - want)) < 1e-13
+
+
+def test_group_plan_rejects_target_outside_tile():
+    g = O.OGate("h", 11)
+    plan = ctypes.c_void_p()
+    assert lib.hq_group_plan_create(12, 0x3FF, pack([g]), 1, ctypes.byref(plan)) != 0
+    assert b"not inside the tile" in lib.hq_last_error()
+
+
+def test_scalar_and_empty_groups():
+    n = 12
+    plan = ctypes.c_void_p()
+    scal = O.OGate("id", -1, mat=np.array([[0.6 + 0.8j, 0], [0, 0.6 + 0.8j]]))
+    check(lib.hq_group_plan_create(n, 0xFFF, pack([scal]), 1, ctypes.byref(plan)))
+    st = random_state(n, 9)
+    want = st * (0.6 + 0.8j)
+    check(lib.hq_debug_group_plan_emulate(plan, st.ctypes.data))
+    assert np.max(np.abs(st - want)) < 1e-15
+    lib.hq_group_plan_destroy(plan)
+    check(lib.hq_group_plan_create(n, 0xFFF, None, 0, ctypes.byref(plan)))
+    st2 = random_state(n, 10)
+    keep = st2.copy()
+    check(lib.hq_debug_group_plan_emulate(plan, st2.ctypes.data))
+    assert np.array_equal(st2, keep)
+    lib.hq_group_plan_destroy(plan)
+
+
+def emulate_circuit(text):
+    api.init_host_only(1, 0)
+    c = api.Circuit.from_qasm(text)
+    c.compile()
+    n = c.num_qubits
+    s = O.zero_state(n)
+    check(lib.hq_debug_circuit_emulate(c._h, s.ctypes.data))
+    info = c.schedule_info()
+    c.close()
+    return n, s, info
+
+
+@pytest.mark.parametrize("name", ["qft_16", "bv_16", "hidden_shift_16", "supremacy_16", "quantum_volume_14", "qaoa_16",
+                                  "adder_16", "basis_change_14"])
+def test_compiled_schedule_matches_oracle(name):
+    text = C.generate(name)
+    n, got, info = emulate_circuit(text)
+    _, gates = O.parse_qasm(text)
+    assert info["gates"] == len(gates)          # every gate lands in exactly one group
+    want = O.simulate(n, gates)
+    assert np.max(np.abs(got - want)) < 1e-12
+
+
+@pytest.mark.parametrize("n,seed", [(10, 1), (11, 2), (13, 3), (17, 4)])
+def test_compiled_random_circuits(n, seed):
+    text = C.random_circuit(n, 500, seed, names=["h", "x", "y", "z", "s", "sdg", "t", "tdg", "rx", "ry", "rz", "u1", "u3",
+                                                  "cx", "cy", "cz", "crx", "cry", "crz", "cu1", "ccx"])
+    _, got, _ = emulate_circuit(text)
+    _, gates = O.parse_qasm(text)
+    assert np.max(np.abs(got - O.simulate(n, gates))) < 1e-12
+
+
+def test_schedule_shapes_of_reference_benchmarks():
+    """Sweeps per circuit stay in the range the reference's own partitioner produces."""
+    api.init_host_only(1, 0)
+    for name, max_groups in [("qft_28", 5), ("bv_28", 5), ("hidden_shift_28", 5), ("supremacy_30", 14)]:
+        c = api.Circuit.from_qasm(C.generate(name))
+        info = c.plan_only()
+        assert info["stages"] == 1 and 1 <= info["groups"] <= max_groups, (name, info)
+        c.close()
