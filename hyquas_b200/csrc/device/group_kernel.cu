@@ -4,14 +4,20 @@
 // tile of the local state (the amplitudes whose tile_mask bits vary while all other bits are fixed)
 // apply, in order, a list of single-/controlled-qubit gates, in place.  How it does it is new:
 //
-//   * persistent CTAs, one producer warp + NT consumer threads; the producer streams tiles into a
-//     ring of shared-memory buffers with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx),
-//     one copy per contiguous run of the tile, so HBM reads are asynchronous and never touch registers;
-//   * the host splits the gate list into ROUNDS.  In a round every consumer thread holds 16 amplitudes
+//   * persistent CTAs (several per SM) loop over tiles; a tile is brought into shared memory by 1-D TMA
+//     bulk copies (cp.async.bulk ... mbarrier::complete_tx, one per contiguous run of the tile), issued
+//     as soon as the previous tile's last shared-memory read is done, so the HBM read of tile i+1 overlaps
+//     the last round of arithmetic and the write-back of tile i (and the other CTAs of the SM);
+//   * the host splits the gate list into ROUNDS.  In a round every thread holds 16 amplitudes
 //     (4 "register qubits") in registers and applies all gates of the round there: no shared-memory
 //     traffic and no barrier per gate (the reference does one SMEM read-modify-write plus a
 //     __syncthreads() per gate, kernelOpt.cu:214-386).  Between rounds the tile is re-laid-out through
 //     shared memory (XOR-swizzled, conflict-free 128-bit accesses) to change the register qubits;
+//   * the lowered op list lives in shared memory; every (arithmetic class, target register bit, control
+//     register bit) combination is its own straight-line body selected by one jump, so a gate costs its
+//     FP64 instructions plus a handful of decode instructions;
+//   * diagonal gates that touch no register qubit of the round commute with everything else in it; they are
+//     folded, per thread, into ONE complex factor (a "diagonal run") applied with a single multiply pass;
 //   * controls and diagonal targets may sit on register bits, thread bits, or bits outside the tile
 //     (the reference's "block bits"); they become predicate masks over the physical index;
 //   * the last round writes registers straight back to HBM with 128-bit stores.
@@ -19,7 +25,10 @@
 // Algorithmic traffic: 32 bytes per amplitude per launch (16 read + 16 written), independent of the
 // number of gates.
 #include <algorithm>
+#include <cmath>
+#include <complex>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "hq_internal.h"
@@ -35,9 +44,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -60,249 +66,131 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-template <int NT>
-__device__ __forceinline__ void consumer_sync() {
-    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-}
 
 // ---- in-register gate arithmetic -----------------------------------------------------------------
-#define HQ_PAIR_LOOP(TB)                                                     \
-    _Pragma("unroll") for (int p = 0; p < R / 2; ++p) {                      \
-        const int lo = ((p >> (TB)) << ((TB) + 1)) | (p & ((1 << (TB)) - 1)); \
-        const int hi = lo | (1 << (TB));                                     \
-        if ((lo & creg) == creg)
+// The 16 amplitudes of a thread live in named PTX registers (hqa0..hqa31) declared once per kernel; all
+// arithmetic on them is generated inline PTX (group_ops_gen.inc, produced by tools/gen_group_ops.py) that
+// updates them IN PLACE, so the op loop carries no C++-visible state and a gate costs only its FP64 work.
+//   real 2x2 [[a,b],[c,d]] on scalars (u,v):  v <- c*u + d*v ; u <- (det/d)*u + (b/d)*v   (LU form, 4 FP64, no temporary)
+//   the host prepares c, d, det/d, b/d and keeps |d| away from 0 by factoring M = X * (X M) when needed.
+}  // namespace hq
+#include "group_ops_gen.inc"
+namespace hq {
 
-template <int TB>
-__device__ __forceinline__ void op_gen(double2 (&a)[R], const DevOp& o, uint32_t creg) {
-    const double r00 = o.m[0], i00 = o.m[1], r01 = o.m[2], i01 = o.m[3];
-    const double r10 = o.m[4], i10 = o.m[5], r11 = o.m[6], i11 = o.m[7];
-    HQ_PAIR_LOOP(TB) {
-        const double2 x = a[lo], y = a[hi];
-        a[lo].x = fma(-i01, y.y, fma(r01, y.x, fma(-i00, x.y, r00 * x.x)));
-        a[lo].y = fma(r01, y.y, fma(i01, y.x, fma(r00, x.y, i00 * x.x)));
-        a[hi].x = fma(-i11, y.y, fma(r11, y.x, fma(-i10, x.y, r10 * x.x)));
-        a[hi].y = fma(r11, y.y, fma(i11, y.x, fma(r10, x.y, i10 * x.x)));
-    }}
-}
-template <int TB>
-__device__ __forceinline__ void op_real(double2 (&a)[R], const DevOp& o, uint32_t creg) {
-    const double r00 = o.m[0], r01 = o.m[2], r10 = o.m[4], r11 = o.m[6];
-    HQ_PAIR_LOOP(TB) {
-        const double2 x = a[lo], y = a[hi];
-        a[lo].x = fma(r01, y.x, r00 * x.x);
-        a[lo].y = fma(r01, y.y, r00 * x.y);
-        a[hi].x = fma(r11, y.x, r10 * x.x);
-        a[hi].y = fma(r11, y.y, r10 * x.y);
-    }}
-}
-template <int TB>
-__device__ __forceinline__ void op_rxl(double2 (&a)[R], const DevOp& o, uint32_t creg) {
-    const double r00 = o.m[0], i01 = o.m[3], i10 = o.m[5], r11 = o.m[6];
-    HQ_PAIR_LOOP(TB) {
-        const double2 x = a[lo], y = a[hi];
-        a[lo].x = fma(-i01, y.y, r00 * x.x);
-        a[lo].y = fma(i01, y.x, r00 * x.y);
-        a[hi].x = fma(-i10, x.y, r11 * y.x);
-        a[hi].y = fma(i10, x.x, r11 * y.y);
-    }}
-}
-template <int TB>
-__device__ __forceinline__ void op_swap(double2 (&a)[R], uint32_t creg) {
-    HQ_PAIR_LOOP(TB) {
-        const double2 x = a[lo];
-        a[lo] = a[hi];
-        a[hi] = x;
-    }}
-}
-template <int TB>
-__device__ __forceinline__ void op_yl(double2 (&a)[R], uint32_t creg) {
-    HQ_PAIR_LOOP(TB) {
-        const double2 x = a[lo], y = a[hi];
-        a[lo] = make_double2(y.y, -y.x);
-        a[hi] = make_double2(-x.y, x.x);
-    }}
-}
-template <int TB>
-__device__ __forceinline__ void op_diag_r(double2 (&a)[R], const DevOp& o, uint32_t creg) {
-    const double r0 = o.m[0], i0 = o.m[1], r1 = o.m[6], i1 = o.m[7];
-    const bool skip_lo = o.flags & 1u;
-    HQ_PAIR_LOOP(TB) {
-        if (!skip_lo) {
-            const double2 x = a[lo];
-            a[lo].x = fma(-i0, x.y, r0 * x.x);
-            a[lo].y = fma(i0, x.x, r0 * x.y);
-        }
-        const double2 y = a[hi];
-        a[hi].x = fma(-i1, y.y, r1 * y.x);
-        a[hi].y = fma(i1, y.x, r1 * y.y);
-    }}
+// diag(d0,d1) on a thread/outside bit with register-bit controls (rare: e.g. CRZ with the control in registers)
+__device__ __forceinline__ void op_diag_t(const DevOp& o, uint64_t phys) {
+    const bool hi = (o.tphys == 0) || (phys & o.tphys);
+    if (!hi && (o.flags & 1u)) return;
+    hq_cmul_masked(hi ? o.m[6] : o.m[0], hi ? o.m[7] : o.m[1], o.creg);
 }
 
-#define HQ_TB_SWITCH(CALL)          \
-    switch (o.tbit) {               \
-        case 0: CALL(0); break;     \
-        case 1: CALL(1); break;     \
-        case 2: CALL(2); break;     \
-        default: CALL(3); break;    \
+// A run of diagonal gates none of which touches a register bit: every amplitude of the thread gets the same factor.
+__device__ __forceinline__ void op_diag_run(const DevOp* entries, int n, uint64_t phys) {
+    double fr = 1.0, fi = 0.0;
+    bool any = false;
+    for (int e = 0; e < n; ++e) {
+        const DevOp& o = entries[e];
+        if ((phys & o.cphys) != o.cphys) continue;
+        const bool hi = (o.tphys == 0) || (phys & o.tphys);
+        if (!hi && (o.flags & 1u)) continue;
+        const double dr = hi ? o.m[6] : o.m[0], di = hi ? o.m[7] : o.m[1];
+        const double nr = fma(-fi, di, fr * dr);
+        fi = fma(fi, dr, fr * di);
+        fr = nr;
+        any = true;
     }
-
-__device__ __forceinline__ void apply_op(double2 (&a)[R], const DevOp& o, uint64_t phys) {
-    if ((phys & o.cphys) != o.cphys) return;
-    const uint32_t creg = o.creg;
-    switch (o.kind) {
-        case OP_GEN: {
-#define C_(TB) op_gen<TB>(a, o, creg)
-            HQ_TB_SWITCH(C_)
-#undef C_
-            break;
-        }
-        case OP_REAL: {
-#define C_(TB) op_real<TB>(a, o, creg)
-            HQ_TB_SWITCH(C_)
-#undef C_
-            break;
-        }
-        case OP_RXL: {
-#define C_(TB) op_rxl<TB>(a, o, creg)
-            HQ_TB_SWITCH(C_)
-#undef C_
-            break;
-        }
-        case OP_SWAP: {
-#define C_(TB) op_swap<TB>(a, creg)
-            HQ_TB_SWITCH(C_)
-#undef C_
-            break;
-        }
-        case OP_YL: {
-#define C_(TB) op_yl<TB>(a, creg)
-            HQ_TB_SWITCH(C_)
-#undef C_
-            break;
-        }
-        case OP_DIAG_R: {
-#define C_(TB) op_diag_r<TB>(a, o, creg)
-            HQ_TB_SWITCH(C_)
-#undef C_
-            break;
-        }
-        default: {  // OP_DIAG_T
-            const bool hi = (o.tphys == 0) || (phys & o.tphys);
-            if (!hi && (o.flags & 1u)) return;
-            const double fr = hi ? o.m[6] : o.m[0], fi = hi ? o.m[7] : o.m[1];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                if ((i & creg) == creg) {
-                    const double2 x = a[i];
-                    a[i].x = fma(-fi, x.y, fr * x.x);
-                    a[i].y = fma(fi, x.x, fr * x.y);
-                }
-            }
-            break;
-        }
-    }
-}
-
-__device__ __forceinline__ DevOp load_op(const DevOp* p) {
-    DevOp o;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&o);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(DevOp) / 16); ++i) d[i] = __ldg(s + i);
-    return o;
+    if (any) hq_cmul_all(fr, fi);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__((1 << (K - RBITS)) + 32, 1) group_kernel(const __grid_constant__ GroupParams P) {
+__device__ __forceinline__ void issue_tile_load(const GroupParams& P, uint64_t t, double2* tile, uint64_t* bar,
+                                                uint64_t* tbase_s, int lane) {
+    uint64_t base = 0;
+    for (int s = 0; s < P.nseg; ++s) base |= ((t >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
+    if (lane == 0) {
+        *tbase_s = base;
+        mbar_arrive_expect_tx(bar, (16u << K));
+    }
+    __syncwarp();
+    const uint32_t run_amps = P.run_bytes >> 4;
+    for (int q = lane; q < P.nruns; q += 32)
+        tma_bulk_g2s(tile + (size_t)q * run_amps, P.state + base + __ldg(P.run_off + q), P.run_bytes, bar);
+}
+
+template <int K, int MINB>
+__global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __grid_constant__ GroupParams P) {
     constexpr int NT = 1 << (K - RBITS);
     constexpr int TILE = 1 << K;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2* tiles = reinterpret_cast<double2*>(smem_raw);                          // NBUF * TILE amplitudes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NBUF * TILE * 16);  // full[NBUF], empty[NBUF]
-    uint64_t* tbase_s = bars + 2 * NBUF;                                            // tile base per buffer
-    DevRound* rounds_s = reinterpret_cast<DevRound*>(tbase_s + NBUF);               // nrounds
+    double2* tile = reinterpret_cast<double2*>(smem_raw);                              // TILE amplitudes
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILE * 16);        // "tile landed" mbarrier
+    uint64_t* tbase_s = bar + 1;                                                       // base index of the landed tile
+    DevRound* rounds_s = reinterpret_cast<DevRound*>(bar + 2);
+    DevOp* ops_s = reinterpret_cast<DevOp*>(rounds_s + P.nrounds);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int b = 0; b < NBUF; ++b) {
-            mbar_init(&bars[b], 1);
-            mbar_init(&bars[NBUF + b], NT / 32);
-        }
+        mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.rounds);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(rounds_s);
-        const int words = P.nrounds * (int)(sizeof(DevRound) / 4);
-        for (int i = tid; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+    {   // stage the round descriptors and the op list once per CTA
+        const uint4* src = reinterpret_cast<const uint4*>(P.rounds);
+        uint4* dst = reinterpret_cast<uint4*>(rounds_s);
+        const int n16 = P.nrounds * (int)(sizeof(DevRound) / 16);
+        for (int i = tid; i < n16; i += NT) dst[i] = __ldg(src + i);
+        src = reinterpret_cast<const uint4*>(P.ops);
+        dst = reinterpret_cast<uint4*>(ops_s);
+        const int m16 = P.nops * (int)(sizeof(DevOp) / 16);
+        for (int i = tid; i < m16; i += NT) dst[i] = __ldg(src + i);
     }
     __syncthreads();
 
-    if (tid >= NT) {
-        // ---------------- producer warp: TMA bulk loads ----------------
-        const int lane = tid - NT;
-        uint32_t it = 0;
-        for (uint64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++it) {
-            const uint32_t buf = it % NBUF, use = it / NBUF;
-            if (use > 0) mbar_wait(&bars[NBUF + buf], (use - 1) & 1);
-            uint64_t base = 0;
-            for (int s = 0; s < P.nseg; ++s) base |= ((t >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
-            if (lane == 0) {
-                tbase_s[buf] = base;
-                mbar_arrive_expect_tx(&bars[buf], (uint32_t)TILE * 16u);
-            }
-            __syncwarp();
-            const uint32_t run_amps = P.run_bytes >> 4;
-            for (int q = lane; q < P.nruns; q += 32)
-                tma_bulk_g2s(tiles + (size_t)buf * TILE + (size_t)q * run_amps, P.state + base + __ldg(P.run_off + q),
-                             P.run_bytes, &bars[buf]);
-        }
-        return;
-    }
+    uint64_t t = blockIdx.x;
+    if (t < P.ntiles && tid < 32) issue_tile_load<K>(P, t, tile, bar, tbase_s, tid);
 
-    // ---------------- consumers ----------------
-    double2 a[R];
-    uint32_t it = 0;
-    for (uint64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++it) {
-        const uint32_t buf = it % NBUF, use = it / NBUF;
-        mbar_wait(&bars[buf], use & 1);
-        const uint64_t tbase = tbase_s[buf];
-        double2* sm = tiles + (size_t)buf * TILE;
+    HQ_DECLARE_AMP_REGS();
+    const uint32_t tile_s = smem_u32(tile);
+    for (uint32_t it = 0; t < P.ntiles; t += gridDim.x, ++it) {
+        mbar_wait(bar, it & 1);
+        const uint64_t tbase = *tbase_s;
         for (int r = 0; r < P.nrounds; ++r) {
             const DevRound& rd = rounds_s[r];
             const uint32_t tin = __ldg(P.tb + (size_t)(2 * r) * NT + tid);
             const uint64_t phys = tbase | __ldg(P.gt + (size_t)r * NT + tid);
-#pragma unroll
-            for (int i = 0; i < R; ++i) a[i] = sm[tin ^ rd.ro_in[i]];
+            hq_load_amps(tile_s, tin, rd.ro_in);
 
-            int op = rd.op_begin;
-            const int op_end = rd.op_end;
-            if (op < op_end) {
-                DevOp cur = load_op(P.ops + op);
-                for (; op < op_end; ++op) {
-                    DevOp nxt;
-                    if (op + 1 < op_end) nxt = load_op(P.ops + op + 1);
-                    apply_op(a, cur, phys);
-                    if (op + 1 < op_end) cur = nxt;
-                }
+            const bool last = rd.flags & 2u;
+            if (last) {
+                // every thread has its amplitudes in registers: the buffer can take the next tile now, so its HBM
+                // read runs under this round's arithmetic and write-back
+                fence_proxy_async();
+                __syncthreads();
+                const uint64_t tn = t + gridDim.x;
+                if (tn < P.ntiles && tid < 32) issue_tile_load<K>(P, tn, tile, bar, tbase_s, tid);
             }
 
-            if (rd.flags & 2u) {
-                // last round: this thread is done with the buffer -> release it to the producer, then
-                // write the 16 amplitudes back to HBM with 128-bit stores
-                fence_proxy_async();
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&bars[NBUF + buf]);
-                double2* g = P.state + phys;
-#pragma unroll
-                for (int i = 0; i < R; ++i) g[rd.go[i]] = a[i];
+            const int op_end = rd.op_end;
+            for (int op = rd.op_begin; op < op_end; ++op) {
+                const DevOp& o = ops_s[op];
+                const uint32_t code = o.code;
+                if (code == CODE_DIAG_RUN) {
+                    op_diag_run(&o + 1, (int)o.aux, phys);
+                    op += (int)o.aux;
+                    continue;
+                }
+                if ((phys & o.cphys) != o.cphys) continue;
+                if (code == CODE_DIAG_T) op_diag_t(o, phys);
+                else hq_apply_op(o);
+            }
+
+            if (last) {
+                hq_store_amps_global(P.state + phys, rd.go);
             } else {
                 const uint32_t tout = __ldg(P.tb + (size_t)(2 * r + 1) * NT + tid);
-                if (rd.flags & 1u) consumer_sync<NT>();
-#pragma unroll
-                for (int i = 0; i < R; ++i) sm[tout ^ rd.ro_out[i]] = a[i];
-                consumer_sync<NT>();
+                if (rd.flags & 1u) __syncthreads();
+                hq_store_amps(tile_s, tout, rd.ro_out);
+                __syncthreads();
             }
         }
     }
@@ -345,6 +233,25 @@ static bool classify(const hq_gate& g, HostGate& h) {
     return true;
 }
 
+// Coefficients of the in-place LU update for M = [[a,b],[c,d]]:  {c, d, e = det/d, f = b/d}.
+//   OP_REAL: M real, out = 4 doubles.   OP_RXL: M = [[a, i b'],[i c', d]]; out describes the real matrix
+//   [[a,-b'],[c',d]] (the partner uses -c, -f).   OP_GEN: complex, out = 4 complex numbers.
+static void encode_lu(uint32_t kind, const double* M, double* out) {
+    std::memset(out, 0, 8 * sizeof(double));
+    if (kind == OP_REAL || kind == OP_RXL) {
+        const double a = M[0], d = M[6];
+        const double b = kind == OP_REAL ? M[2] : -M[3];
+        const double c = kind == OP_REAL ? M[4] : M[5];
+        out[0] = c; out[1] = d; out[2] = (a * d - b * c) / d; out[3] = b / d;
+        return;
+    }
+    typedef std::complex<double> C;
+    const C a(M[0], M[1]), b(M[2], M[3]), c(M[4], M[5]), d(M[6], M[7]);
+    const C e = (a * d - b * c) / d, f = b / d;
+    out[0] = c.real(); out[1] = c.imag(); out[2] = d.real(); out[3] = d.imag();
+    out[4] = e.real(); out[5] = e.imag(); out[6] = f.real(); out[7] = f.imag();
+}
+
 }  // namespace hq
 
 using namespace hq;
@@ -357,7 +264,6 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
     const int K = popcount64(tile_mask);
     HQ_REQUIRE(K >= 10 && K <= 12, "tile_mask must select 10, 11 or 12 bits");
     HQ_REQUIRE(L >= K && L <= 40, "local qubit count out of range for the gate-group kernel");
-    
     HQ_REQUIRE((tile_mask >> L) == 0, "tile_mask has bits outside the local state");
     HQ_REQUIRE((tile_mask & ((1ull << MIN_RUN_BITS) - 1)) == ((1ull << MIN_RUN_BITS) - 1),
                "tile_mask must contain the low hq_group_min_run_bits() bits");
@@ -422,7 +328,6 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
         }
     }
     const int nrounds = (int)rounds.size();
-    HQ_REQUIRE(nrounds <= 200, "too many rounds in one gate group");
 
     // ---- encode ----
     std::vector<DevRound> drounds(nrounds);
@@ -434,20 +339,95 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
         int reg_of_tile[16];
         for (int i = 0; i < 16; ++i) reg_of_tile[i] = -1;
         for (int b = 0; b < RBITS; ++b) reg_of_tile[rd.reg[b]] = b;
-        // thread-id bits -> tile bits: ascending, but the first three get distinct (bit mod 3) so that a
-        // quarter-warp covers all eight 16-byte bank groups of the swizzled layout
+
+        // lower the round's gates first: the thread-bit assignment below wants to know which tile bits act as
+        // thread-level predicates
+        std::vector<DevOp> body, run;
+        uint32_t predicate_tile_bits = 0;
+        for (int gi : rd.gates) {
+            const HostGate& h = hg[gi];
+            DevOp o{};
+            std::memcpy(o.m, h.m, sizeof(o.m));
+            // A controlled diag(1,d) is symmetric in its qubits, so any of them may play "target": prefer one that
+            // is a register bit (then the others are plain predicates).
+            int tgt = h.target_phys, ctl[2] = {h.c1_phys, h.c2_phys};
+            const bool d0one = h.diag && h.m[0] == 1.0 && h.m[1] == 0.0;
+            auto in_reg = [&](int phys) { return phys >= 0 && phys_to_tile[phys] >= 0 && reg_of_tile[phys_to_tile[phys]] >= 0; };
+            if (h.diag && d0one && tgt >= 0 && !in_reg(tgt))
+                for (int& c : ctl) if (in_reg(c)) { std::swap(tgt, c); break; }
+            for (int c : ctl) {
+                if (c < 0) continue;
+                if (in_reg(c)) o.creg |= 1u << reg_of_tile[phys_to_tile[c]];
+                else { o.cphys |= 1ull << c; if (phys_to_tile[c] >= 0) predicate_tile_bits |= 1u << phys_to_tile[c]; }
+            }
+            const int ncreg = popcount64(o.creg);
+            const uint32_t cbc = ncreg == 0 ? 0 : (ncreg == 1 ? 1 + (uint32_t)__builtin_ctz(o.creg) : CBC_GENERIC);
+            if (h.diag) {
+                if (d0one) o.flags |= 1u;
+                if (in_reg(tgt)) {
+                    const uint32_t tbit = reg_of_tile[phys_to_tile[tgt]];
+                    const bool zflip = d0one && h.m[6] == -1.0 && h.m[7] == 0.0;
+                    o.code = op_code(zflip ? OP_ZFLIP : OP_DIAG_R, tbit, cbc);
+                    body.push_back(o);
+                } else {
+                    o.tphys = tgt >= 0 ? 1ull << tgt : 0;
+                    if (tgt >= 0 && phys_to_tile[tgt] >= 0) predicate_tile_bits |= 1u << phys_to_tile[tgt];
+                    o.code = CODE_DIAG_T;
+                    (o.creg == 0 ? run : body).push_back(o);   // no register bit involved: joins the diagonal run
+                }
+            } else {
+                const uint32_t tbit = reg_of_tile[phys_to_tile[tgt]];
+                const bool generic_only = h.kind == OP_GEN || h.kind == OP_REAL || h.kind == OP_RXL || h.kind == OP_YL;
+                const uint32_t cb = (generic_only && cbc != 0) ? CBC_GENERIC : cbc;
+                if (h.kind == OP_SWAP || h.kind == OP_YL) {
+                    o.code = op_code(h.kind, tbit, cb);
+                    body.push_back(o);
+                } else {
+                    // in-place LU form needs a diagonal entry d that is not small; otherwise apply X*M first and
+                    // then X (a register swap):  M = X * (X*M)
+                    double M[8];
+                    std::memcpy(M, h.m, sizeof(M));
+                    const double dmag = std::hypot(M[6], M[7]);
+                    const bool flip = dmag < 0.35;
+                    if (flip) for (int k = 0; k < 4; ++k) std::swap(M[k], M[4 + k]);   // rows exchanged
+                    const uint32_t kind = (flip && h.kind == OP_RXL) ? (uint32_t)OP_GEN : h.kind;   // X*M leaves the RX-like form
+                    encode_lu(kind, M, o.m);
+                    o.code = op_code(kind, tbit, cb);
+                    body.push_back(o);
+                    if (flip) {
+                        DevOp x = o;
+                        std::memset(x.m, 0, sizeof(x.m));
+                        x.code = op_code(OP_SWAP, tbit, cbc);
+                        body.push_back(x);
+                    }
+                }
+            }
+        }
+
+        // thread-id bits -> tile bits.  Constraints: the first three lane bits get distinct (bit mod 3) so that a
+        // quarter-warp covers all eight 16-byte bank groups of the swizzled layout; round 0 reads the linear TMA
+        // image, so it wants tile bits 0,1,2 on lanes 0..2; the last round stores to HBM, so its lanes are the
+        // lowest tile bits (contiguous 512-byte warp stores).  Otherwise prefer bits that are NOT predicates on the
+        // lanes, so that controlled gates switch whole warps on/off instead of diverging inside a warp.
+        std::vector<int> free_bits;
+        for (int b = 0; b < K; ++b) if (reg_of_tile[b] < 0) free_bits.push_back(b);
         std::vector<int> tbits;
-        for (int b = 0; b < K; ++b) if (reg_of_tile[b] < 0) tbits.push_back(b);
-        {
+        const bool is_last = r == nrounds - 1, lin_in = r == 0;
+        if (is_last) {
+            tbits = free_bits;
+        } else {
+            std::vector<int> pref = free_bits;
+            std::stable_sort(pref.begin(), pref.end(), [&](int x, int y) {
+                return (predicate_tile_bits >> x & 1) < (predicate_tile_bits >> y & 1);
+            });
             std::vector<int> first;
             bool used_res[3] = {false, false, false};
-            for (int b : tbits) if (!used_res[b % 3] && (int)first.size() < 3) { first.push_back(b); used_res[b % 3] = true; }
-            if (r == 0 && tbits.size() >= 3 && tbits[0] == 0 && tbits[1] == 1 && tbits[2] == 2) first = {0, 1, 2};
-            std::vector<int> ordered = first;
-            for (int b : tbits) if (std::find(first.begin(), first.end(), b) == first.end()) ordered.push_back(b);
-            tbits.swap(ordered);
+            if (lin_in) { for (int b : free_bits) if (b < 3) { first.push_back(b); used_res[b % 3] = true; } }
+            for (int b : pref) if ((int)first.size() < 3 && !used_res[b % 3]) { first.push_back(b); used_res[b % 3] = true; }
+            tbits = first;
+            for (int b : pref) if (std::find(tbits.begin(), tbits.end(), b) == tbits.end()) tbits.push_back(b);
         }
-        const bool lin_in = (r == 0);
+
         DevRound& d = drounds[r];
         std::memset(&d, 0, sizeof(d));
         for (int i = 0; i < R; ++i) {
@@ -465,29 +445,16 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
             gt[(size_t)r * NT + t] = pdep64(j, tile_mask);
         }
         d.op_begin = (int)dops.size();
-        for (int gi : rd.gates) {
-            const HostGate& h = hg[gi];
-            DevOp o{};
-            std::memcpy(o.m, h.m, sizeof(o.m));
-            o.kind = h.kind;
-            for (int c : {h.c1_phys, h.c2_phys}) {
-                if (c < 0) continue;
-                const int tc = phys_to_tile[c];
-                if (tc >= 0 && reg_of_tile[tc] >= 0) o.creg |= 1u << reg_of_tile[tc];
-                else o.cphys |= 1ull << c;
-            }
-            if (h.diag) {
-                if (h.m[0] == 1.0 && h.m[1] == 0.0) o.flags |= 1u;
-                const int tt = h.target_phys >= 0 ? phys_to_tile[h.target_phys] : -1;
-                if (tt >= 0 && reg_of_tile[tt] >= 0) { o.kind = OP_DIAG_R; o.tbit = reg_of_tile[tt]; }
-                else { o.kind = OP_DIAG_T; o.tphys = h.target_phys >= 0 ? 1ull << h.target_phys : 0; }
-            } else {
-                o.tbit = reg_of_tile[phys_to_tile[h.target_phys]];
-            }
-            dops.push_back(o);
+        if (!run.empty()) {   // the run commutes with every other op of the round (it touches no register bit)
+            DevOp hdr{};
+            hdr.code = CODE_DIAG_RUN;
+            hdr.aux = (uint32_t)run.size();
+            dops.push_back(hdr);
+            dops.insert(dops.end(), run.begin(), run.end());
         }
+        dops.insert(dops.end(), body.begin(), body.end());
         d.op_end = (int)dops.size();
-        d.flags = (lin_in && nrounds > 1 ? 1u : 0u) | (r == nrounds - 1 ? 2u : 0u);
+        d.flags = (lin_in && nrounds > 1 ? 1u : 0u) | (is_last ? 2u : 0u);
     }
 
     // ---- tile geometry ----
@@ -499,14 +466,15 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
 
     auto* plan = new hq_group_plan();
     plan->L = L; plan->K = K; plan->NT = NT; plan->tile_mask = tile_mask;
-    plan->nrounds = nrounds; plan->nops = (int)dops.size();
+    plan->nrounds = nrounds; plan->nops = (int)dops.size(); plan->ngates = (int)hg.size();
     GroupParams& p = plan->p;
     p.ntiles = 1ull << (L - K);
     p.nruns = nruns;
     p.run_bytes = 16u << run_bits;
     p.nrounds = nrounds;
+    p.nops = (int)dops.size();
     {   // tile number -> base: scatter over the runs of bits NOT in the tile
-        const uint64_t outmask = ((L == 64 ? ~0ull : (1ull << L) - 1)) & ~tile_mask;
+        const uint64_t outmask = ((1ull << L) - 1) & ~tile_mask;
         int nseg = 0, src = 0, b = 0;
         while (b < L) {
             if (!(outmask >> b & 1)) { ++b; continue; }
@@ -516,6 +484,12 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
             src += e - b; ++nseg; b = e;
         }
         p.nseg = nseg;
+    }
+    plan->smem = (size_t)(16u << K) + 16 + (size_t)nrounds * sizeof(DevRound) + dops.size() * sizeof(DevOp);
+    if (plan->smem > 227 * 1024) {
+        delete plan;
+        set_error("gate group does not fit in shared memory (too many gates/rounds for one launch): split it");
+        return HQ_ERR_ARG;
     }
 
     // one device blob: run_off | rounds | ops | gt | tb
@@ -546,22 +520,27 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
         p.gt = reinterpret_cast<const uint64_t*>(d + o_gt);
         p.tb = reinterpret_cast<const uint16_t*>(d + o_tb);
     }
-
-    plan->smem = (size_t)NBUF * (16u << K) + (2 * NBUF + NBUF) * 8 + (size_t)nrounds * sizeof(DevRound) + 128;
-    const uint64_t want = (uint64_t)(rt().ready ? rt().sm_count : 148) * (K <= 11 ? 2 : 1);
-    plan->grid = (int)std::min<uint64_t>(p.ntiles, want);
     *out = plan;
     return HQ_OK;
 }
 
-template <int K>
+template <int K, int MINB>
 static int launch_k(const hq_group_plan* plan, GroupParams p, cudaStream_t s) {
     static bool attr_set = false;
+    static std::map<size_t, int> occupancy;   // dynamic smem bytes -> resident CTAs per SM
+    auto kern = group_kernel<K, MINB>;
     if (!attr_set) {
-        HQ_CUDA(cudaFuncSetAttribute(group_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    group_kernel<K><<<plan->grid, plan->NT + 32, plan->smem, s>>>(p);
+    auto it = occupancy.find(plan->smem);
+    if (it == occupancy.end()) {
+        int nb = 0;
+        HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, plan->NT, plan->smem));
+        it = occupancy.emplace(plan->smem, std::max(1, nb)).first;
+    }
+    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)rt().sm_count * it->second);
+    kern<<<plan->grid, plan->NT, plan->smem, s>>>(p);
     HQ_CUDA(cudaGetLastError());
     return HQ_OK;
 }
@@ -569,14 +548,14 @@ static int launch_k(const hq_group_plan* plan, GroupParams p, cudaStream_t s) {
 extern "C" int hq_group_plan_launch(const hq_group_plan* plan, void* state, int on_comm_stream) {
     HQ_REQUIRE(plan != nullptr && state != nullptr, "null plan or state");
     HQ_REQUIRE(rt().ready && plan->dev_blob != nullptr, "plan was created without a bound GPU (call hq_init first)");
-    HQ_REQUIRE(plan->smem <= 227 * 1024, "gate group needs more shared memory than one SM has");
     GroupParams p = plan->p;
     p.state = static_cast<double2*>(state);
     cudaStream_t s = on_comm_stream ? rt().comm : rt().compute;
+    const bool relaxed = rt().relaxed_regs;   // fewer resident CTAs, no register cap (HQ_RELAXED_REGS=1)
     switch (plan->K) {
-        case 10: return launch_k<10>(plan, p, s);
-        case 11: return launch_k<11>(plan, p, s);
-        case 12: return launch_k<12>(plan, p, s);
+        case 10: return relaxed ? launch_k<10, 6>(plan, p, s) : launch_k<10, 8>(plan, p, s);
+        case 11: return relaxed ? launch_k<11, 3>(plan, p, s) : launch_k<11, 4>(plan, p, s);
+        case 12: return relaxed ? launch_k<12, 1>(plan, p, s) : launch_k<12, 2>(plan, p, s);
         default: set_error("unsupported tile size"); return HQ_ERR_UNSUPPORTED;
     }
 }

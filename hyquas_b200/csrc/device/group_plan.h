@@ -8,11 +8,11 @@
 namespace hq {
 
 constexpr int RBITS = 4;          // register qubits per round
-constexpr int R = 1 << RBITS;     // amplitudes per consumer thread
-constexpr int NBUF = 3;           // TMA ring depth
+constexpr int R = 1 << RBITS;     // amplitudes per thread
 constexpr int MAX_SEG = 24;
 constexpr int MIN_RUN_BITS = 3;   // tiles are made of >= 128-byte contiguous runs
 
+// Arithmetic classes.  Classes < OPK_TEMPLATED are instantiated per (target register bit, control case).
 enum OpKind : uint32_t {
     OP_GEN = 0,     // general complex 2x2 on a register bit
     OP_REAL,        // real 2x2 (H, RY, ...)
@@ -20,17 +20,26 @@ enum OpKind : uint32_t {
     OP_SWAP,        // X / CNOT / CCX
     OP_YL,          // [[0, -i],[i, 0]]
     OP_DIAG_R,      // diag(d0, d1), target is a register bit
-    OP_DIAG_T,      // diag(d0, d1), target is a thread/outside bit (or none: scalar)
+    OP_ZFLIP,       // diag(1, -1) on a register bit: sign flips only (Z / CZ)
+    OPK_TEMPLATED,
+    OP_DIAG_T = OPK_TEMPLATED,   // diag(d0, d1) whose target is a thread/outside bit, with register-bit controls
+    OP_DIAG_RUN,                 // header of `aux` following entries: diagonal gates that touch no register bit
 };
+// control case of a templated op: 0 = no register-bit control, 1..4 = exactly register bit (cbc-1), 5 = generic mask
+constexpr uint32_t CBC_GENERIC = 5;
+#define HQ_OP_CODE(kind, tb, cbc) ((uint32_t)(kind) * 24u + (uint32_t)(tb) * 6u + (uint32_t)(cbc))
+inline uint32_t op_code(uint32_t kind, uint32_t tb, uint32_t cbc) { return HQ_OP_CODE(kind, tb, cbc); }
+constexpr uint32_t CODE_DIAG_T = OPK_TEMPLATED * 24;
+constexpr uint32_t CODE_DIAG_RUN = CODE_DIAG_T + 1;
 
 struct alignas(16) DevOp {
-    double m[8];
-    uint32_t kind;
-    uint32_t tbit;     // register-index bit of the target (OP_DIAG_T: unused)
-    uint32_t creg;     // controls that are register-index bits
-    uint32_t flags;    // bit0: d0 == 1 (skip the lo half of a diagonal)
+    double m[8];       // row-major 2x2 (re, im); diagonal ops use m[0..1] = d0, m[6..7] = d1
+    uint32_t code;     // op_code(kind, tbit, cbc) / CODE_DIAG_T / CODE_DIAG_RUN
+    uint32_t creg;     // all register-index control bits
+    uint32_t flags;    // bit0: d0 == 1 (the "lo" half of a diagonal is untouched)
+    uint32_t aux;      // CODE_DIAG_RUN: number of entries that follow
     uint64_t cphys;    // controls outside the registers, as a mask over the physical local index
-    uint64_t tphys;    // OP_DIAG_T: physical bit of the target (0 = scalar, always d1)
+    uint64_t tphys;    // diagonal ops with a non-register target: its physical bit (0 = scalar, always d1)
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
 
@@ -54,6 +63,7 @@ struct GroupParams {
     int32_t nruns;
     uint32_t run_bytes;
     int32_t nrounds;
+    int32_t nops;
     int32_t nseg;
     uint8_t seg_shift[MAX_SEG];  // tile number -> tile base: base |= ((t >> seg_src) & seg_mask) << seg_shift
     uint8_t seg_src[MAX_SEG];
@@ -65,7 +75,8 @@ struct GroupParams {
 struct hq_group_plan {
     int L = 0, K = 0, NT = 0;
     uint64_t tile_mask = 0;
-    int nrounds = 0, nops = 0, grid = 0;
+    int nrounds = 0, nops = 0, ngates = 0;
+    mutable int grid = 0;
     size_t smem = 0;
     std::vector<unsigned char> blob;      // host image of the device tables (run_off | rounds | ops | gt | tb)
     size_t o_run = 0, o_rounds = 0, o_ops = 0, o_gt = 0, o_tb = 0;

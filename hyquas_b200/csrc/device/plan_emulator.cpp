@@ -5,6 +5,9 @@
 // group_kernel<K> instruction for instruction but serially.  It exists so that the `-m "not gpu"` tests can
 // prove the planner's encoding against the oracle on a machine without a GPU; GPU parity tests go through
 // hq_group_plan_launch.  It is deliberately slow and is not exported in include/hyquas_b200.h's product section.
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -16,47 +19,78 @@ using namespace hq;
 namespace {
 struct Amp { double x, y; };
 
-void applyOp(Amp* a, const DevOp& o, uint64_t phys) {
-    if ((phys & o.cphys) != o.cphys) return;
-    const uint32_t creg = o.creg;
-    if (o.kind == OP_DIAG_T) {
-        const bool hi = (o.tphys == 0) || (phys & o.tphys);
-        if (!hi && (o.flags & 1u)) return;
-        const double fr = hi ? o.m[6] : o.m[0], fi = hi ? o.m[7] : o.m[1];
-        for (int i = 0; i < R; ++i)
-            if ((i & creg) == creg) { Amp x = a[i]; a[i].x = fr * x.x - fi * x.y; a[i].y = fr * x.y + fi * x.x; }
-        return;
+void cmul(Amp& v, double fr, double fi) { Amp x = v; v.x = fr * x.x - fi * x.y; v.y = fr * x.y + fi * x.x; }
+
+// returns how many extra entries were consumed (diagonal runs)
+int applyOp(Amp* a, const DevOp* op, uint64_t phys) {
+    const DevOp& o = *op;
+    if (o.code == CODE_DIAG_RUN) {
+        double fr = 1.0, fi = 0.0;
+        for (uint32_t e = 1; e <= o.aux; ++e) {
+            const DevOp& d = op[e];
+            if ((phys & d.cphys) != d.cphys) continue;
+            const bool hi = (d.tphys == 0) || (phys & d.tphys);
+            if (!hi && (d.flags & 1u)) continue;
+            const double dr = hi ? d.m[6] : d.m[0], di = hi ? d.m[7] : d.m[1];
+            const double nr = fr * dr - fi * di;
+            fi = fi * dr + fr * di;
+            fr = nr;
+        }
+        for (int i = 0; i < R; ++i) cmul(a[i], fr, fi);
+        return (int)o.aux;
     }
-    const int tb = (int)o.tbit;
+    if ((phys & o.cphys) != o.cphys) return 0;
+    const uint32_t creg = o.creg;
+    if (o.code == CODE_DIAG_T) {
+        const bool hi = (o.tphys == 0) || (phys & o.tphys);
+        if (!hi && (o.flags & 1u)) return 0;
+        for (int i = 0; i < R; ++i)
+            if ((i & creg) == creg) cmul(a[i], hi ? o.m[6] : o.m[0], hi ? o.m[7] : o.m[1]);
+        return 0;
+    }
+    const uint32_t kind = o.code / 24, tb = (o.code % 24) / 6, cbc = o.code % 6;
+    // the templated control case must agree with the full mask the planner stored
+    const uint32_t expect = cbc == 0 ? 0u : (cbc <= 4 ? 1u << (cbc - 1) : creg);
+    if (expect != creg) { std::fprintf(stderr, "plan emulator: control case %u disagrees with mask %u\n", cbc, creg); std::abort(); }
     for (int p = 0; p < R / 2; ++p) {
         const int lo = ((p >> tb) << (tb + 1)) | (p & ((1 << tb) - 1)), hi = lo | (1 << tb);
         if ((lo & creg) != creg) continue;
         const Amp x = a[lo], y = a[hi];
         const double* m = o.m;
-        switch (o.kind) {
-            case OP_GEN:
-                a[lo].x = m[0] * x.x - m[1] * x.y + m[2] * y.x - m[3] * y.y;
-                a[lo].y = m[0] * x.y + m[1] * x.x + m[2] * y.y + m[3] * y.x;
-                a[hi].x = m[4] * x.x - m[5] * x.y + m[6] * y.x - m[7] * y.y;
-                a[hi].y = m[4] * x.y + m[5] * x.x + m[6] * y.y + m[7] * y.x;
+        switch (kind) {
+            case OP_GEN: {   // m = {c, d, e, f} complex: hi <- c*lo + d*hi ; lo <- e*lo + f*hi
+                const std::complex<double> c(m[0], m[1]), d(m[2], m[3]), ee(m[4], m[5]), f(m[6], m[7]);
+                std::complex<double> lo_(x.x, x.y), hi_(y.x, y.y);
+                hi_ = c * lo_ + d * hi_;
+                lo_ = ee * lo_ + f * hi_;
+                a[lo] = {lo_.real(), lo_.imag()}; a[hi] = {hi_.real(), hi_.imag()};
                 break;
-            case OP_REAL:
-                a[lo].x = m[0] * x.x + m[2] * y.x; a[lo].y = m[0] * x.y + m[2] * y.y;
-                a[hi].x = m[4] * x.x + m[6] * y.x; a[hi].y = m[4] * x.y + m[6] * y.y;
+            }
+            case OP_REAL: {  // m = {c, d, e, f} real
+                Amp l = x, h2 = y;
+                h2.x = m[0] * l.x + m[1] * h2.x; l.x = m[2] * l.x + m[3] * h2.x;
+                h2.y = m[0] * l.y + m[1] * h2.y; l.y = m[2] * l.y + m[3] * h2.y;
+                a[lo] = l; a[hi] = h2;
                 break;
-            case OP_RXL:
-                a[lo].x = m[0] * x.x - m[3] * y.y; a[lo].y = m[0] * x.y + m[3] * y.x;
-                a[hi].x = m[6] * y.x - m[5] * x.y; a[hi].y = m[6] * y.y + m[5] * x.x;
+            }
+            case OP_RXL: {   // (lo.x, hi.y) with {c,d,e,f}; (lo.y, hi.x) with {-c,d,e,-f}
+                Amp l = x, h2 = y;
+                h2.y = m[0] * l.x + m[1] * h2.y; l.x = m[2] * l.x + m[3] * h2.y;
+                h2.x = -m[0] * l.y + m[1] * h2.x; l.y = m[2] * l.y - m[3] * h2.x;
+                a[lo] = l; a[hi] = h2;
                 break;
+            }
             case OP_SWAP: a[lo] = y; a[hi] = x; break;
             case OP_YL: a[lo] = {y.y, -y.x}; a[hi] = {-x.y, x.x}; break;
             case OP_DIAG_R:
-                if (!(o.flags & 1u)) { a[lo].x = m[0] * x.x - m[1] * x.y; a[lo].y = m[0] * x.y + m[1] * x.x; }
-                a[hi].x = m[6] * y.x - m[7] * y.y; a[hi].y = m[6] * y.y + m[7] * y.x;
+                if (!(o.flags & 1u)) cmul(a[lo], m[0], m[1]);
+                cmul(a[hi], m[6], m[7]);
                 break;
-            default: break;
+            case OP_ZFLIP: a[hi] = {-y.x, -y.y}; break;
+            default: std::fprintf(stderr, "plan emulator: bad op code %u\n", o.code); std::abort();
         }
     }
+    return 0;
 }
 }  // namespace
 
@@ -87,7 +121,7 @@ extern "C" int hq_debug_group_plan_emulate(const hq_group_plan* plan, double* st
             for (int tid = 0; tid < NT; ++tid) {
                 Amp* a = &regs[(size_t)tid * R];
                 const uint64_t phys = base | gt[(size_t)r * NT + tid];
-                for (int op = rd.op_begin; op < rd.op_end; ++op) applyOp(a, ops[op], phys);
+                for (int op = rd.op_begin; op < rd.op_end; ++op) op += applyOp(a, &ops[op], phys);
                 if (rd.flags & 2u) {
                     for (int i = 0; i < R; ++i) state[phys + rd.go[i]] = a[i];
                 } else {

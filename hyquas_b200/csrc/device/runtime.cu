@@ -96,6 +96,7 @@ extern "C" int hq_init(int device) {
         const int k = atoi(e);
         if (k >= 10 && k <= 12) r.tile_bits = k;
     }
+    if (const char* e = getenv("HQ_RELAXED_REGS")) r.relaxed_regs = atoi(e) != 0;
     r.ready = true;
     return HQ_OK;
 }
