@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhyquas_b200.so")
+# HQ_LIB_SUFFIX selects an alternative build of the same library (kernel A/B experiments, e.g. "_r4")
+LIB_PATH = os.path.join(_HERE, "libhyquas_b200" + os.environ.get("HQ_LIB_SUFFIX", "") + ".so")
 
 
 class HqGate(ctypes.Structure):
@@ -57,6 +58,8 @@ _SIGS = {
     "hq_group_plan_table_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
+    "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),
+    "hq_microbench_copy": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
     "hq_timer_start": (_c.c_int, []),
     "hq_timer_stop_ms": (_c.c_int, [_P(_c.c_float)]),
     # circuit layer -- include/hyquas_b200_circuit.h

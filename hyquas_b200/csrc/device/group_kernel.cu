@@ -74,7 +74,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   real 2x2 [[a,b],[c,d]] on scalars (u,v):  v <- c*u + d*v ; u <- (det/d)*u + (b/d)*v   (LU form, 4 FP64, no temporary)
 //   the host prepares c, d, det/d, b/d and keeps |d| away from 0 by factoring M = X * (X M) when needed.
 }  // namespace hq
-#include "group_ops_gen.inc"
+#if HQ_RBITS == 4
+#include "group_ops_gen_r4.inc"
+#else
+#include "group_ops_gen_r3.inc"
+#endif
 namespace hq {
 
 // diag(d0,d1) on a thread/outside bit with register-bit controls (rare: e.g. CRZ with the control in registers)
@@ -328,6 +332,7 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
         }
     }
     const int nrounds = (int)rounds.size();
+    const bool trace_plan = getenv("HQ_TRACE_PLAN") != nullptr;
 
     // ---- encode ----
     std::vector<DevRound> drounds(nrounds);
@@ -454,6 +459,12 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
         }
         dops.insert(dops.end(), body.begin(), body.end());
         d.op_end = (int)dops.size();
+        if (trace_plan) {   // developer aid: which bodies does this round execute?
+            fprintf(stderr, "[plan] round %d/%d regs={", r, nrounds);
+            for (int b = 0; b < RBITS; ++b) fprintf(stderr, "%d%s", rd.reg[b], b + 1 < RBITS ? "," : "} ops:");
+            for (int i = d.op_begin; i < d.op_end; ++i) fprintf(stderr, " %u", dops[i].code);
+            fprintf(stderr, "\n");
+        }
         d.flags = (lin_in && nrounds > 1 ? 1u : 0u) | (is_last ? 2u : 0u);
     }
 
@@ -552,10 +563,12 @@ extern "C" int hq_group_plan_launch(const hq_group_plan* plan, void* state, int 
     p.state = static_cast<double2*>(state);
     cudaStream_t s = on_comm_stream ? rt().comm : rt().compute;
     const bool relaxed = rt().relaxed_regs;   // fewer resident CTAs, no register cap (HQ_RELAXED_REGS=1)
+    // resident CTAs per SM asked of ptxas: 2048 threads' worth of registers at 64 (RBITS=3) / 128 (RBITS=4) per thread
+    constexpr int B12 = RBITS == 4 ? 2 : 2, B11 = 2 * B12, B10 = 4 * B12;
     switch (plan->K) {
-        case 10: return relaxed ? launch_k<10, 6>(plan, p, s) : launch_k<10, 8>(plan, p, s);
-        case 11: return relaxed ? launch_k<11, 3>(plan, p, s) : launch_k<11, 4>(plan, p, s);
-        case 12: return relaxed ? launch_k<12, 1>(plan, p, s) : launch_k<12, 2>(plan, p, s);
+        case 10: return relaxed ? launch_k<10, B10 * 3 / 4>(plan, p, s) : launch_k<10, B10>(plan, p, s);
+        case 11: return relaxed ? launch_k<11, B11 * 3 / 4>(plan, p, s) : launch_k<11, B11>(plan, p, s);
+        case 12: return relaxed ? launch_k<12, 1>(plan, p, s) : launch_k<12, B12>(plan, p, s);
         default: set_error("unsupported tile size"); return HQ_ERR_UNSUPPORTED;
     }
 }

@@ -7,7 +7,10 @@
 
 namespace hq {
 
-constexpr int RBITS = 4;          // register qubits per round
+#ifndef HQ_RBITS
+#define HQ_RBITS 4
+#endif
+constexpr int RBITS = HQ_RBITS;   // register qubits per round (3 or 4; build-time choice)
 constexpr int R = 1 << RBITS;     // amplitudes per thread
 constexpr int MAX_SEG = 24;
 constexpr int MIN_RUN_BITS = 3;   // tiles are made of >= 128-byte contiguous runs

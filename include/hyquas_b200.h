@@ -89,6 +89,11 @@ int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates,
 int hq_timer_start(void);
 int hq_timer_stop_ms(float* ms);
 
+/* ---- B200 microbenchmarks feeding the evaluator (replaces evaluator-preprocess/process.cpp:85-165, which times
+ *      cublasZgemm and cuTT; here: FP64 FMA rate (kind 0), FP64 tensor-core mma.sync rate (kind 1), copy bandwidth) */
+int hq_microbench_fp64(int kind, double* tflops);
+int hq_microbench_copy(void* state, int L, double* gbs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,12 +7,15 @@ join and ptxas ends up copying the whole set once per gate (measured: 65 % of al
 Here the amplitudes live in named PTX registers (hqa0..hqa31) that the C++ compiler never sees; every op body
 updates them in place, so a gate costs its FP64 instructions and nothing else.
 
-    python tools/gen_group_ops.py > hyquas_b200/csrc/device/group_ops_gen.inc
+    python tools/gen_group_ops.py 4 > hyquas_b200/csrc/device/group_ops_gen_r4.inc     (argument = register qubits per thread)
 
 Register naming: amplitude i (0..15) = (hqa{2i}, hqa{2i+1}) = (re, im).
 Op numbering must match group_plan.h: code = kind*24 + tb*6 + cbc, cbc: 0 none, 1..4 register bit cbc-1, 5 generic.
 """
-R = 16
+import sys
+
+RBITS = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+R = 1 << RBITS
 KINDS = ["GEN", "REAL", "RXL", "SWAP", "YL", "DIAG_R", "ZFLIP"]
 GENERIC_ONLY = {"GEN", "REAL", "RXL", "YL"}   # single-control cases are routed to the generic mask on the host
 
@@ -121,7 +124,7 @@ def emit_body(kind, tb, cbc):
         stmts = []
         sel = []
         for lo, hi in pairs(tb):
-            if 1 <= cbc <= 4 and not (lo >> (cbc - 1)) & 1:
+            if 1 <= cbc <= RBITS and not (lo >> (cbc - 1)) & 1:
                 continue
             ls, names = pair_body(var, lo, hi)
             sel.append((lo, ls))
@@ -152,7 +155,7 @@ def emit_body(kind, tb, cbc):
 def main():
     print("// GENERATED by tools/gen_group_ops.py -- do not edit.  See that script for the why and the register naming.")
     print("// clang-format off")
-    print('#define HQ_DECLARE_AMP_REGS() asm volatile(".reg .f64 hqa<32>;")')
+    print(f'#define HQ_DECLARE_AMP_REGS() asm volatile(".reg .f64 hqa<{2 * R}>;")')
     print()
     # loads / stores
     print("// tile (shared memory, 32-bit shared address of amplitude index 0) <-> amplitude registers")
@@ -187,9 +190,9 @@ def main():
     print()
     cases = []
     for k, kind in enumerate(KINDS):
-        for tb in range(4):
+        for tb in range(RBITS):
             for cbc in range(6):
-                if 1 <= cbc <= 4 and (cbc - 1 == tb or kind in GENERIC_ONLY):
+                if 1 <= cbc <= 4 and (cbc - 1 == tb or cbc > RBITS or kind in GENERIC_ONLY):
                     continue
                 code = k * 24 + tb * 6 + cbc
                 print(f"__device__ __forceinline__ void hq_op_{code}(const hq::DevOp& o) {{   // {kind} tb={tb} cbc={cbc}")

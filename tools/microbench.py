@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""B200 microbenchmarks of the gate-group kernel: synthetic single-purpose circuits, per-launch CUDA-event times.
+
+    python tools/microbench.py [--qubits 30] [--out gpurun_out/microbench.json]
+
+Each case is a tiny circuit built through the public API; the numbers are ms per gate-group launch over 2^n amplitudes.
+Used (a) to calibrate the evaluator (tools/calibrate.py reads the JSON) and (b) as kernel A/B evidence.
+"""
+import argparse
+import ctypes
+import json
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hyquas_b200 import api  # noqa: E402
+from hyquas_b200._lib import check, lib  # noqa: E402
+
+
+def build(n, spec, count, qubits, seed=1):
+    rng = random.Random(seed)
+    c = api.Circuit(n)
+    for i in range(count):
+        name = spec[i % len(spec)]
+        q = qubits[i % len(qubits)]
+        if name in ("H", "X", "Y", "Z", "S", "T", "SDG", "TDG"):
+            c.add_gate(name, q)
+        elif name in ("RX", "RY", "RZ", "U1"):
+            c.add_gate(name, q, params=(rng.uniform(0.1, 3.0),))
+        elif name == "U3":
+            c.add_gate(name, q, params=(rng.uniform(0.1, 3.0), rng.uniform(0.1, 3.0), rng.uniform(0.1, 3.0)))
+        elif name in ("CZ", "CNOT", "CY"):
+            q2 = qubits[(i + 1) % len(qubits)]
+            c.add_gate(name, q, q2)
+        elif name in ("CRX", "CRY", "CRZ", "CU1"):
+            q2 = qubits[(i + 1) % len(qubits)]
+            c.add_gate(name, q, q2, params=(rng.uniform(0.1, 3.0),))
+        else:
+            raise ValueError(name)
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qubits", type=int, default=30)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    n = args.qubits
+    api.init()
+    res = {"qubits": n, "lib_suffix": os.environ.get("HQ_LIB_SUFFIX", ""), "cases": {}}
+    v = ctypes.c_double()
+    for kind, key in ((0, "fp64_fma_tflops"), (1, "fp64_mma_tflops")):
+        check(lib.hq_microbench_fp64(kind, v))
+        res[key] = v.value
+    st = ctypes.c_void_p()
+    check(lib.hq_state_alloc(n, ctypes.byref(st)))
+    check(lib.hq_microbench_copy(st, n, v))
+    res["copy_gbs"] = v.value
+    check(lib.hq_state_free(st))
+    print(json.dumps({k: res[k] for k in ("fp64_fma_tflops", "fp64_mma_tflops", "copy_gbs")}), flush=True)
+
+    hi4 = [8, 9, 10, 11]
+    cases = {
+        "sweep_1gate": (["H"], 1, [8]),
+        "h_x64_4q": (["H"], 64, hi4),
+        "rx_x64_4q": (["RX"], 64, hi4),
+        "u3_x64_4q": (["U3"], 64, hi4),
+        "t_x64_4q": (["T"], 64, hi4),
+        "rz_x64_4q": (["RZ"], 64, hi4),
+        "x_x64_4q": (["X"], 64, hi4),
+        "cz_x64_4q": (["CZ"], 64, hi4),
+        "cnot_x64_4q": (["CNOT"], 64, hi4),
+        "mix5_x64_4q": (["H", "RX", "T", "RY", "CZ"], 64, hi4),
+        "h_x64_1q": (["H"], 64, [9]),
+        "h_x96_12q": (["H"], 96, list(range(12))),
+        "mix5_x96_12q": (["H", "RX", "T", "RY", "CZ"], 96, list(range(12))),
+        "u3_x96_12q": (["U3"], 96, list(range(12))),
+        "h_x16_4q": (["H"], 16, hi4),
+        "h_x256_4q": (["H"], 256, hi4),
+    }
+    for name, (spec, count, qubits) in cases.items():
+        c = build(n, spec, count, qubits)
+        c.compile()
+        c.prepare_state()
+        for _ in range(2):
+            c.execute()
+        _, ms, per = c.execute(per_group=True)
+        _, ms2, per2 = c.execute(per_group=True)
+        per = [min(a, b) for a, b in zip(per, per2)]
+        res["cases"][name] = {"gates": count, "groups": len(per), "ms_total": min(ms, ms2), "per_group_ms": per}
+        print(f"{name:16s} gates={count:4d} groups={len(per)} total={min(ms, ms2):8.3f} ms  per-group={['%.2f' % x for x in per]}",
+              flush=True)
+        c.close()
+    if args.out:
+        json.dump(res, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
