@@ -60,6 +60,18 @@ _SIGS = {
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
     "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),
     "hq_microbench_copy": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
+    "hq_comm_unique_id": (_c.c_int, [_c.c_void_p]),
+    "hq_comm_init": (_c.c_int, [_c.c_int, _c.c_int, _c.c_void_p]),
+    "hq_comm_info": (_c.c_int, [_P(_c.c_int), _P(_c.c_int)]),
+    "hq_comm_destroy": (_c.c_int, []),
+    "hq_comm_bcast_host": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int]),
+    "hq_comm_allgather_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t]),
+    "hq_state_bitswap": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int)]),
+    "hq_swap_plan_create": (_c.c_int, [_c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_void_p)]),
+    "hq_swap_begin": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_swap_wait_chunk": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
+    "hq_swap_end": (_c.c_int, [_c.c_void_p]),
+    "hq_swap_plan_destroy": (_c.c_int, [_c.c_void_p]),
     "hq_timer_start": (_c.c_int, []),
     "hq_timer_stop_ms": (_c.c_int, [_P(_c.c_float)]),
     # circuit layer -- include/hyquas_b200_circuit.h
@@ -81,10 +93,17 @@ _SIGS = {
     "hq_circuit_schedule_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
     "hq_circuit_dump": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _P(_c.c_size_t)]),
     "hq_circuit_amplitudes": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_circuit_local_shard": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_circuit_final_layout": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_circuit_logger_flush": (_c.c_int, [_c.c_char_p, _c.c_size_t]),
     "hq_circuit_destroy": (_c.c_int, [_c.c_void_p]),
     # test hook (device/plan_emulator.cpp) -- used by the CPU test-suite only
     "hq_debug_group_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_debug_num_stages": (_c.c_int, [_c.c_void_p]),
+    "hq_debug_stage_swap": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int),
+                                       _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_debug_stage_emulate": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "hq_debug_final_pos": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -123,6 +123,18 @@ class Circuit:
             raise HyquasError(lib.hq_circuit_last_error().decode())
         return out
 
+    def local_shard(self, world: int) -> np.ndarray:
+        """This process' shard (physical order); needs run(destroy=False)."""
+        g = world.bit_length() - 1
+        out = np.empty(1 << (self.num_qubits - g), dtype=np.complex128)
+        check(lib.hq_circuit_local_shard(self._h, out.ctypes.data))
+        return out
+
+    def final_layout(self):
+        pos = (ctypes.c_int * self.num_qubits)()
+        check(lib.hq_circuit_final_layout(self._h, pos))
+        return list(pos)
+
     def close(self) -> None:
         if self._h:
             lib.hq_circuit_destroy(self._h)

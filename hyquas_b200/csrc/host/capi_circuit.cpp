@@ -173,6 +173,22 @@ extern "C" int hq_circuit_amplitudes(hq_circuit* h, double* out_re_im) {
     return HQ_OK;
 }
 
+// This process' shard in PHYSICAL order (2^(n - log2 world) amplitudes) and the final layout pos[logical] = physical:
+// what a multi-process host needs to assemble or spot-check the distributed state (Circuit::run's copy_back +
+// toPhysicalID, src/circuit.cpp:54-63,95-104).
+extern "C" int hq_circuit_local_shard(hq_circuit* h, double* out_re_im) {
+    if (!h || !out_re_im) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    if (!h->c->localShard(out_re_im)) { g_cerr = "state not resident (run with destroy=0)"; return HQ_ERR_UNSUPPORTED; }
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_final_layout(hq_circuit* h, int* pos) {
+    if (!h || !pos) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    const State& st = h->c->getSchedule().finalState;
+    for (int i = 0; i < h->c->numQubits; i++) pos[i] = st.pos[i];
+    return HQ_OK;
+}
+
 extern "C" int hq_circuit_logger_flush(char* buf, size_t cap) {
     std::string all;
     for (const auto& s : Logger::pending()) all += "Logger: " + s + "\n";
@@ -195,6 +211,48 @@ extern "C" int hq_circuit_destroy(hq_circuit* h) {
 // plan with the plan emulator (device/plan_emulator.cpp).  Validates partitioner + lowering + round planner
 // without a GPU; the product path launches the CUDA kernels instead.
 extern "C" int hq_debug_group_plan_emulate(const hq_group_plan* plan, double* state_re_im);
+// Stepwise variant for the multi-process CPU tests (world_size-2 gloo): the test moves the data between ranks itself,
+// following the stage's SwapPlan, and asks this hook to replay the stage's gate groups on its shard.
+//   hq_debug_stage_swap:    the swap that establishes `stage` (npairs local bit transpositions, then k (local, global) trades)
+//   hq_debug_stage_emulate: phase 0 = overlap groups on chunk `chunk` (pointer = start of the shard), phase 1 = full groups
+//   hq_debug_final_pos:     pos[logical qubit] = physical bit after the last stage
+extern "C" int hq_debug_num_stages(hq_circuit* h) { return h ? (int)h->c->getSchedule().localGroups.size() : -1; }
+extern "C" int hq_debug_stage_swap(hq_circuit* h, int stage, int* npairs, int* pa, int* pb, int* k, int* lbits, int* gbits,
+                                   int* noverlap) {
+    if (!h || stage < 0 || stage >= (int)h->c->getSchedule().localGroups.size()) { g_cerr = "bad stage"; return HQ_ERR_ARG; }
+    const LocalGroup& lg = h->c->getSchedule().localGroups[stage];
+    *npairs = (int)lg.swap.localPerm.size();
+    for (int i = 0; i < *npairs; i++) { pa[i] = lg.swap.localPerm[i].first; pb[i] = lg.swap.localPerm[i].second; }
+    *k = (int)lg.swap.localBit.size();
+    for (int i = 0; i < *k; i++) { lbits[i] = lg.swap.localBit[i]; gbits[i] = lg.swap.globalBit[i]; }
+    if (noverlap) *noverlap = (int)lg.overlapGroups.size();
+    return HQ_OK;
+}
+extern "C" int hq_debug_stage_emulate(hq_circuit* h, int stage, int phase, int chunk, double* state_re_im) {
+    if (!h || !state_re_im || stage < 0 || stage >= (int)h->c->getSchedule().localGroups.size()) { g_cerr = "bad stage"; return HQ_ERR_ARG; }
+    const LocalGroup& lg = h->c->getSchedule().localGroups[stage];
+    const int L = h->c->numQubits - MyGlobalVars::bit, k = (int)lg.swap.localBit.size();
+    if (phase == 0) {
+        double* base = state_re_im + 2 * ((size_t)chunk << (L - k));
+        for (const auto& gg : lg.overlapGroups) {
+            int rc = hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(chunk)), base);
+            if (rc != HQ_OK) return rc;
+        }
+    } else {
+        for (const auto& gg : lg.fullGroups) {
+            int rc = hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(0)), state_re_im);
+            if (rc != HQ_OK) return rc;
+        }
+    }
+    return HQ_OK;
+}
+extern "C" int hq_debug_final_pos(hq_circuit* h, int* pos) {
+    if (!h || !pos) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    const State& st = h->c->getSchedule().finalState;
+    for (int i = 0; i < h->c->numQubits; i++) pos[i] = st.pos[i];
+    return HQ_OK;
+}
+
 extern "C" int hq_debug_circuit_emulate(hq_circuit* h, double* state_re_im) {
     if (!h || !state_re_im) { g_cerr = "null argument"; return HQ_ERR_ARG; }
     if (MyGlobalVars::numGPUs != 1) { g_cerr = "emulation hook is single-process"; return HQ_ERR_UNSUPPORTED; }

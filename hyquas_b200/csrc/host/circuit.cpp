@@ -41,7 +41,7 @@ void Circuit::compile() {
     Logger::add("Total Groups: %d %d %d %d", int(schedule.localGroups.size()), fullGroups, fullGates, overlapGates);
     if (getenv("HQ_SHOW_SCHEDULE")) schedule.dump(numQubits);
     auto t1 = chrono::system_clock::now();
-    Executor::prepare(schedule, numQubits);
+    Executor::prepare(schedule, numQubits, MyGlobalVars::hostOnly);
     auto t2 = chrono::system_clock::now();
     const int d1 = (int)chrono::duration_cast<chrono::microseconds>(t1 - t0).count();
     const int d2 = (int)chrono::duration_cast<chrono::microseconds>(t2 - t1).count();
@@ -204,6 +204,13 @@ void Circuit::printState() {
     if (MyMPI::rank != 0) return;
     fputs(stateDump().c_str(), stdout);
     fflush(stdout);
+}
+
+bool Circuit::localShard(double* out) {
+    if (deviceStateVec.empty()) return false;
+    const int L = numQubits - MyGlobalVars::bit;
+    checkHq(hq_state_download(deviceStateVec[0], L, 0, qindex(1) << L, out));
+    return true;
 }
 
 bool Circuit::fullState(std::vector<qComplex>& out) {

@@ -37,6 +37,7 @@ public:
     const Schedule& getSchedule() const { return schedule; }
     const std::vector<Gate>& getGates() const { return gates; }
     bool fullState(std::vector<qComplex>& out);       // all 2^n amplitudes in LOGICAL order (single process, small n)
+    bool localShard(double* out);                     // this process' amplitudes in PHYSICAL order
     double lastDeviceMs = 0;                          // CUDA-event time of the last run()
     void prepareState();                              // (re)allocate + |0..0>
     int execute(std::vector<float>* perGroupMs = nullptr);   // the timed part of run() on the resident state

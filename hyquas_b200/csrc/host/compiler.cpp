@@ -70,6 +70,10 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
     tileBits = std::min(hq_group_tile_bits(), numLocal);
     pinnedBits = std::min(5, tileBits);
     if (const char* e = getenv("HQ_PINNED_BITS")) pinnedBits = std::max(hq_group_min_run_bits(), std::min(atoi(e), tileBits));
+    overlapSlack = 1.0;
+    if (const char* e = getenv("HQ_OVERLAP_SLACK")) overlapSlack = atof(e);
+    enableOverlap = true;
+    if (const char* e = getenv("HQ_ENABLE_OVERLAP")) enableOverlap = atoi(e) != 0;
     maxGroupGates = 384;
     if (const char* e = getenv("HQ_MAX_GROUP_GATES")) maxGroupGates = std::max(1, atoi(e));
 }
@@ -169,6 +173,7 @@ Schedule Compiler::run() {
     Schedule schedule;
     State state(numQubits);
     std::vector<Stage> stages = splitStages();
+    // pass 1: layouts and swaps (independent of how stages are cut into groups)
     for (size_t s = 0; s < stages.size(); s++) {
         LocalGroup lg;
         lg.relatedQubits = stages[s].locals;
@@ -185,9 +190,49 @@ Schedule Compiler::run() {
             lg.swap = hyquas::planSwap(state, stages[s].locals, numQubits, numLocal);
         }
         lg.state = state;
-        lg.fullGroups = cutGroups(stages[s].gates, state, numLocal);
         schedule.localGroups.push_back(std::move(lg));
     }
+    // pass 2: work to hide the exchange behind.  The stage split is greedy, so the head of stage s always needs the
+    // incoming qubits; what CAN run while chunks are still on the wire is the tail of stage s-1: gates that commute
+    // to the end of that stage and whose non-diagonal targets sit below the k swapped positions in the NEW layout.
+    // They are deferred past the swap and run per landed chunk (the reference's moveToNext + overlapGroups,
+    // src/compiler.cpp:34-68, src/executor.cpp:41-47).  Only as many groups as the predicted exchange time hides.
+    for (size_t s = 1; s < stages.size() && enableOverlap; s++) {
+        LocalGroup& lg = schedule.localGroups[s];
+        const int k = (int)lg.swap.localBit.size();
+        if (k == 0 || numLocal - k < 10) continue;
+        qindex lowSet = 0;
+        for (int p = 0; p < numLocal - k; p++) lowSet |= qindex(1) << lg.state.layout[p];
+        std::vector<Gate>& prev = stages[s - 1].gates;
+        std::vector<int> order(prev.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)prev.size() - 1 - (int)i;   // scan from the end
+        std::vector<int> tail = hyquas::runnableGates(prev, order, lowSet, 1 << 30);
+        std::sort(tail.begin(), tail.end());
+        std::vector<Gate> tailGates;
+        for (int gi : tail) tailGates.push_back(prev[gi]);
+        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal - k);
+        const double commMs = Evaluator::getInstance()->perfSwap(numLocal, k);
+        double used = 0;
+        size_t first = cand.size();
+        while (first > 0) {   // longest suffix of the candidate groups that fits under the exchange
+            const double ms = cand[first - 1].predictedMs * (1 << k);   // predictedMs is per chunk
+            if (used + ms > commMs * overlapSlack) break;
+            used += ms;
+            first--;
+        }
+        std::vector<int> ids;
+        for (size_t i = first; i < cand.size(); i++) {
+            for (auto& g : cand[i].gates) ids.push_back(g.gateID);
+            lg.overlapGroups.push_back(cand[i]);
+        }
+        std::sort(ids.begin(), ids.end());
+        std::vector<Gate> rest;
+        for (auto& g : prev) if (!std::binary_search(ids.begin(), ids.end(), g.gateID)) rest.push_back(g);
+        prev.swap(rest);
+    }
+    // pass 3: cut what is left of every stage into full groups
+    for (size_t s = 0; s < stages.size(); s++)
+        schedule.localGroups[s].fullGroups = cutGroups(stages[s].gates, schedule.localGroups[s].state, numLocal);
     schedule.finalState = state;
     return schedule;
 }

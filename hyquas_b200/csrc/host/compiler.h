@@ -22,6 +22,8 @@ public:
     int tileBits;      // qubits per tile of the gate-group kernel
     int pinnedBits;    // lowest physical bits always kept in the tile (contiguous-run length of HBM accesses)
     int maxGroupGates; // cap on gates per group
+    bool enableOverlap; // per-chunk groups under the exchange (reference: ENABLE_OVERLAP)
+    double overlapSlack; // deferred work may take up to this multiple of the predicted exchange time
 private:
     struct Stage { std::vector<Gate> gates; qindex locals; };
     std::vector<Stage> splitStages() const;

@@ -15,6 +15,7 @@ Evaluator::Evaluator() {
     // FP64 lanes x ~1.7 GHz sustained), expressed in ms per 2^30 amplitudes; refined by tools/calibrate.py.
     hbmGBs = 5800.0;
     launchMs = 0.01;
+    nvlinkGBs = 700.0;
     roundMs30 = 0.55;
     const double slot = 1073741824.0 / (148.0 * 64.0 * 1.7e9) * 1e3;   // ms per FP64 slot per amplitude at 2^30
     for (auto& g : gateNs) g = 4 * slot;
@@ -44,6 +45,7 @@ void Evaluator::loadParam(int) {
     while (in >> key) {
         if (key == "hbm_gbs") in >> hbmGBs;
         else if (key == "launch_ms") in >> launchMs;
+        else if (key == "nvlink_gbs") in >> nvlinkGBs;
         else if (key == "round_ms30") in >> roundMs30;
         else if (key == "gate") { int i; double v; in >> i >> v; if (i >= 0 && i < 32) gateNs[i] = v; }
         else if (key == "dense") { int i; double v; in >> i >> v; if (i >= 0 && i < 8) denseMs30[i] = v; }
@@ -64,6 +66,12 @@ double Evaluator::perfPerGate(int numQubits, const GateGroup* gg) {
     std::vector<GateType> tys;
     for (const Gate& g : gg->gates) tys.push_back(g.type);
     return perfPerGate(numQubits, tys);
+}
+
+double Evaluator::perfSwap(int numQubits, int k) {
+    loadParam(numQubits);
+    const double bytes = 16.0 * std::ldexp(1.0, numQubits) * (1.0 - std::ldexp(1.0, -k));
+    return bytes / (nvlinkGBs * 1e9) * 1e3;
 }
 
 double Evaluator::perfBLAS(int numQubits, int blasSize) {

@@ -20,6 +20,9 @@ public:
     double perfPerGate(int numQubits, const std::vector<GateType>& types);
     // predicted milliseconds for one fused dense (TransMM) launch with a 2^blasSize x 2^blasSize matrix
     double perfBLAS(int numQubits, int blasSize);
+    // predicted milliseconds for swapping k local bits with k global bits (NVLink bytes / measured bandwidth)
+    double perfSwap(int numQubits, int k);
+    double nvlinkGBs;                       // per-direction bandwidth of one GPU during the exchange
     bool PerGateOrBLAS(const GateGroup* gg_pergate, const GateGroup* gg_blas, int numQubits, int blasSize);
     void loadParam(int numQubits);          // optional override from $HYQUAS_PARAM_FILE
     // model constants (public so that the calibration tool and tests can read/write them)

@@ -75,10 +75,15 @@ static void preparePerGate(GateGroup& gg, int numQubits, int numLocal, int numCh
     }
 }
 
-void Executor::prepare(Schedule& schedule, int numQubits) {
+void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
     const int L = numQubits - MyGlobalVars::bit;
     for (auto& lg : schedule.localGroups) {
         const int k = (int)lg.swap.localBit.size();
+        if (k > 0 && !lg.swapPlan && hostOnly == false) {
+            hq_swap_plan* sp = nullptr;
+            checkHq(hq_swap_plan_create(L, k, lg.swap.localBit.data(), lg.swap.globalBit.data(), &sp));
+            lg.swapPlan = sp;
+        }
         for (auto& gg : lg.overlapGroups) if (gg.plans.empty()) preparePerGate(gg, numQubits, L - k, 1 << k);
         for (auto& gg : lg.fullGroups) if (gg.plans.empty()) preparePerGate(gg, numQubits, L, 1);
     }
@@ -86,6 +91,8 @@ void Executor::prepare(Schedule& schedule, int numQubits) {
 
 void Executor::release(Schedule& schedule) {
     for (auto& lg : schedule.localGroups) {
+        if (lg.swapPlan) hq_swap_plan_destroy(static_cast<hq_swap_plan*>(lg.swapPlan));
+        lg.swapPlan = nullptr;
         for (auto* groups : {&lg.overlapGroups, &lg.fullGroups})
             for (auto& gg : *groups) {
                 for (void* p : gg.plans) hq_group_plan_destroy(static_cast<hq_group_plan*>(p));
@@ -117,7 +124,7 @@ void Executor::run() {
     for (size_t s = 0; s < schedule.localGroups.size(); s++) {
         LocalGroup& lg = schedule.localGroups[s];
         if (s > 0 && !lg.swap.empty()) {
-            hyquas::SwapExec ex(deviceStateVec[0], numQubits - MyGlobalVars::bit, lg.swap);
+            hyquas::SwapExec ex(deviceStateVec[0], numQubits - MyGlobalVars::bit, lg.swap, lg.swapPlan);
             const int nChunks = 1 << lg.swap.localBit.size();
             ex.begin();
             for (int i = 0; i < nChunks; i++) {

@@ -16,7 +16,7 @@ public:
     Executor(std::vector<qComplex*> deviceStateVec, int numQubits, Schedule& schedule);
     void run();
     std::vector<float>* perGroupMs = nullptr;   // when set: one CUDA-event timing per gate-group launch (MEASURE_STAGE)
-    static void prepare(Schedule& schedule, int numQubits);   // build device plans (idempotent)
+    static void prepare(Schedule& schedule, int numQubits, bool hostOnly = false);   // build device plans (idempotent)
     static void release(Schedule& schedule);                  // destroy device plans
     // Lower one logical gate for the sub-state whose physical index bits >= numLocal equal `highIndex`.
     // Returns false when the gate acts as identity there.

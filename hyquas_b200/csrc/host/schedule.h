@@ -64,6 +64,7 @@ struct LocalGroup {
     std::vector<GateGroup> overlapGroups;   // run per received chunk, overlapped with the exchange
     std::vector<GateGroup> fullGroups;
     qindex relatedQubits = 0;               // logical qubits that are local in this stage
+    void* swapPlan = nullptr;               // device-side hq_swap_plan of this process (built by Executor::prepare)
     bool contains(int i) const { return (relatedQubits >> i) & 1; }
 };
 

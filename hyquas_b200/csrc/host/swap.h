@@ -7,14 +7,16 @@
 struct ResultItem;
 namespace hyquas {
 
+// Creates the NCCL communicator from WORLD_SIZE / RANK unless the embedding host (bench.py through
+// hq_comm_init) already did.  The unique id travels through a file named after the launcher's pid and MASTER_PORT.
 void commInitFromEnv();
-void bcastAmp(qComplex* amp, int ownerRank);            // rank `ownerRank` -> everybody
-void gatherItems(std::vector<ResultItem>& items);  // everybody -> rank 0 (others end up empty)   // WORLD_SIZE/RANK + file rendezvous for the NCCL unique id
+void bcastAmp(qComplex* amp, int ownerRank);       // rank `ownerRank` -> everybody
+void gatherItems(std::vector<ResultItem>& items);  // everybody -> rank 0 (the others end up empty)
 
-// Executes one SwapPlan in place on this process' shard, chunk by chunk, on the comm stream.
+// Executes one SwapPlan in place on this process' shard, chunk by chunk.
 class SwapExec {
 public:
-    SwapExec(qComplex* state, int numLocal, const SwapPlan& plan);
+    SwapExec(qComplex* state, int numLocal, const SwapPlan& plan, void* devicePlan);
     void begin();              // local bit swaps (compute stream) + enqueue the chunked exchange (comm stream)
     int waitNextChunk();       // makes the compute stream wait for the next landed chunk; returns its index
     void end();
@@ -22,7 +24,7 @@ private:
     qComplex* state;
     int numLocal;
     const SwapPlan& plan;
-    int next = 0;
+    void* devicePlan;
 };
 
 }  // namespace hyquas

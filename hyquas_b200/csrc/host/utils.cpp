@@ -12,6 +12,7 @@ namespace MyGlobalVars {
 int numGPUs = 1;
 int localGPUs = 1;
 int bit = 0;
+bool hostOnly = false;
 
 static int envInt(const char* key, int dflt) {
     const char* v = getenv(key);
@@ -35,6 +36,7 @@ void init() {
 }
 
 void initForTest(int worldSize, int rank) {
+    hostOnly = true;
     numGPUs = worldSize;
     localGPUs = 1;
     bit = get_bit(worldSize);

@@ -85,6 +85,26 @@ int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes);   /* size 
 int hq_group_plan_destroy(hq_group_plan* plan);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (replaces the NCCL bootstrap of MyGlobalVars::init,
+ *      src/utils.cpp:46-58, and Executor::transpose + all2all + sliceBarrier, src/executor.cpp:59-179,650-659).
+ *      The swap trades the top k local bits with k global bits IN PLACE: the local state is 2^k contiguous chunks;
+ *      chunk c goes to the rank whose swapped global bits equal c and is replaced by that rank's chunk.  Chunks move
+ *      in pieces through a two-slot staging ring on the comm stream; hq_swap_wait_chunk() orders the compute stream
+ *      behind one chunk at a time so that per-chunk gate groups overlap the rest of the exchange. -------------------- */
+typedef struct hq_swap_plan hq_swap_plan;
+int hq_comm_unique_id(unsigned char out[128]);                       /* ncclGetUniqueId (rank 0), to be broadcast by the host */
+int hq_comm_init(int world, int rank, const unsigned char id[128]);  /* ncclCommInitRank */
+int hq_comm_info(int* world, int* rank);
+int hq_comm_destroy(void);
+int hq_comm_bcast_host(void* buf, size_t bytes, int root);           /* control plane of printState (small host buffers) */
+int hq_comm_allgather_host(const void* send, void* recv, size_t bytes_per_rank);
+int hq_state_bitswap(void* state, int L, int npairs, const int* a, const int* b);   /* in-place local bit permutation */
+int hq_swap_plan_create(int L, int k, const int* local_bits, const int* global_bits, hq_swap_plan** plan);
+int hq_swap_begin(hq_swap_plan* plan, void* state);                  /* enqueue the whole exchange on the comm stream */
+int hq_swap_wait_chunk(hq_swap_plan* plan, int* chunk);              /* compute stream waits for the next landed chunk */
+int hq_swap_end(hq_swap_plan* plan);
+int hq_swap_plan_destroy(hq_swap_plan* plan);
+
 /* ---- timing helpers (cudaEvent pairs on the compute stream; MEASURE_STAGE, src/executor.cpp:406-458) */
 int hq_timer_start(void);
 int hq_timer_stop_ms(float* ms);

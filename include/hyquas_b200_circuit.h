@@ -40,6 +40,8 @@ int hq_circuit_io_bytes(const hq_circuit* c, size_t* h2d_plan_bytes, size_t* d2h
 int hq_circuit_schedule_info(const hq_circuit* c, int* stages, int* groups, int* gates_in_groups);
 int hq_circuit_dump(hq_circuit* c, char* buf, size_t cap, size_t* needed);              /* printState text */
 int hq_circuit_amplitudes(hq_circuit* c, double* out_re_im); /* all 2^n amplitudes, logical order (small n) */
+int hq_circuit_local_shard(hq_circuit* c, double* out_re_im);  /* this process' 2^(n-g) amplitudes, physical order */
+int hq_circuit_final_layout(hq_circuit* c, int* pos);         /* pos[logical qubit] = physical bit (Schedule::finalState) */
 int hq_circuit_logger_flush(char* buf, size_t cap);          /* Logger::print */
 int hq_circuit_destroy(hq_circuit* c);
 
