@@ -60,6 +60,11 @@ _SIGS = {
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
     "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),
     "hq_microbench_copy": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
+    "hq_dense_plan_create": (_c.c_int, [_c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int), _c.c_void_p, _P(_c.c_void_p)]),
+    "hq_dense_plan_launch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int]),
+    "hq_dense_plan_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_double), _P(_c.c_int)]),
+    "hq_dense_plan_destroy": (_c.c_int, [_c.c_void_p]),
+    "hq_dense_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _c.c_void_p]),
     "hq_comm_unique_id": (_c.c_int, [_c.c_void_p]),
     "hq_comm_init": (_c.c_int, [_c.c_int, _c.c_int, _c.c_void_p]),
     "hq_comm_info": (_c.c_int, [_P(_c.c_int), _P(_c.c_int)]),
@@ -91,6 +96,7 @@ _SIGS = {
     "hq_circuit_norm2": (_c.c_int, [_c.c_void_p, _P(_c.c_double)]),
     "hq_circuit_io_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_size_t), _P(_c.c_size_t)]),
     "hq_circuit_schedule_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_circuit_group_info": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_double), _P(_c.c_int), _P(_c.c_int)]),
     "hq_circuit_dump": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _P(_c.c_size_t)]),
     "hq_circuit_amplitudes": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "hq_circuit_local_shard": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
@@ -99,6 +105,7 @@ _SIGS = {
     "hq_circuit_destroy": (_c.c_int, [_c.c_void_p]),
     # test hook (device/plan_emulator.cpp) -- used by the CPU test-suite only
     "hq_debug_group_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_debug_dense_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "hq_debug_num_stages": (_c.c_int, [_c.c_void_p]),
     "hq_debug_stage_swap": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int),
                                        _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),

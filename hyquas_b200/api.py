@@ -79,6 +79,17 @@ class Circuit:
         check(lib.hq_circuit_schedule_info(self._h, st, gr, gg))
         return {"stages": st.value, "groups": gr.value, "gates": gg.value}
 
+    def groups(self):
+        """Per gate group, in execution order: backend ('tile' | 'dense'), gates, evaluator's predicted ms, launches."""
+        out = []
+        for i in range(self.schedule_info()["groups"]):
+            b, g, l, nb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            ms = ctypes.c_double()
+            check(lib.hq_circuit_group_info(self._h, i, b, g, ms, l, nb))
+            out.append({"backend": "dense" if b.value == 2 else "tile", "gates": g.value, "predicted_ms": ms.value,
+                        "launches": l.value, "blocks": nb.value})
+        return out
+
     def run(self, copy_back: bool = False, destroy: bool = False):
         """Circuit::run -> (wall microseconds of the execution phase, CUDA-event milliseconds)."""
         us, ms = ctypes.c_int(), ctypes.c_double()

@@ -184,7 +184,6 @@ struct hq_dense_plan {
     DenseParams p{};
 };
 
-static inline uint64_t pdep_u64(uint64_t v, uint64_t mask) { return pdep64(v, mask); }
 
 // qubit_pos[i]: physical local bit of matrix qubit i (bit i of the row/column index of U);  U column-major
 // (U[row + col * 2^m], like the A operand of the reference's cublasZgemm call), interleaved re/im.

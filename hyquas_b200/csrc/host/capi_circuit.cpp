@@ -153,6 +153,30 @@ extern "C" int hq_circuit_schedule_info(const hq_circuit* h, int* stages, int* g
     return HQ_OK;
 }
 
+// Group i in execution order (overlap groups of a stage first, then its full groups): backend 1 = tile kernel,
+// 2 = fused dense kernel; launches = kernel launches it costs (2^k for a per-chunk group); predicted_ms = evaluator.
+extern "C" int hq_circuit_group_info(const hq_circuit* h, int index, int* backend, int* ngates, double* predicted_ms, int* launches,
+                                     int* nblocks) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    int i = 0;
+    for (const auto& lg : h->c->getSchedule().localGroups) {
+        const int k = (int)lg.swap.localBit.size();
+        for (const auto* groups : {&lg.overlapGroups, &lg.fullGroups})
+            for (const auto& gg : *groups) {
+                if (i++ != index) continue;
+                const bool chunked = groups == &lg.overlapGroups;
+                if (backend) *backend = gg.backend == Backend::BLAS ? 2 : 1;
+                if (ngates) *ngates = (int)gg.gates.size();
+                if (predicted_ms) *predicted_ms = gg.predictedMs * (chunked ? (1 << k) : 1);
+                if (launches) *launches = chunked ? (1 << k) : 1;
+                if (nblocks) *nblocks = (int)gg.blocks.size();
+                return HQ_OK;
+            }
+    }
+    g_cerr = "group index out of range";
+    return HQ_ERR_ARG;
+}
+
 extern "C" int hq_circuit_dump(hq_circuit* h, char* buf, size_t cap, size_t* needed) {
     if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
     h->dump = h->c->stateDump();
@@ -211,6 +235,11 @@ extern "C" int hq_circuit_destroy(hq_circuit* h) {
 // plan with the plan emulator (device/plan_emulator.cpp).  Validates partitioner + lowering + round planner
 // without a GPU; the product path launches the CUDA kernels instead.
 extern "C" int hq_debug_group_plan_emulate(const hq_group_plan* plan, double* state_re_im);
+extern "C" int hq_debug_dense_plan_emulate(const hq_dense_plan* plan, double* state_re_im);
+static int emulateGroup(const GateGroup& gg, int idx, double* state) {
+    if (gg.backend == Backend::BLAS) return hq_debug_dense_plan_emulate(static_cast<const hq_dense_plan*>(gg.plans.at(idx)), state);
+    return hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(idx)), state);
+}
 // Stepwise variant for the multi-process CPU tests (world_size-2 gloo): the test moves the data between ranks itself,
 // following the stage's SwapPlan, and asks this hook to replay the stage's gate groups on its shard.
 //   hq_debug_stage_swap:    the swap that establishes `stage` (npairs local bit transpositions, then k (local, global) trades)
@@ -235,12 +264,12 @@ extern "C" int hq_debug_stage_emulate(hq_circuit* h, int stage, int phase, int c
     if (phase == 0) {
         double* base = state_re_im + 2 * ((size_t)chunk << (L - k));
         for (const auto& gg : lg.overlapGroups) {
-            int rc = hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(chunk)), base);
+            int rc = emulateGroup(gg, chunk, base);
             if (rc != HQ_OK) return rc;
         }
     } else {
         for (const auto& gg : lg.fullGroups) {
-            int rc = hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(0)), state_re_im);
+            int rc = emulateGroup(gg, 0, state_re_im);
             if (rc != HQ_OK) return rc;
         }
     }
@@ -258,7 +287,7 @@ extern "C" int hq_debug_circuit_emulate(hq_circuit* h, double* state_re_im) {
     if (MyGlobalVars::numGPUs != 1) { g_cerr = "emulation hook is single-process"; return HQ_ERR_UNSUPPORTED; }
     for (const auto& lg : h->c->getSchedule().localGroups)
         for (const auto& gg : lg.fullGroups) {
-            int rc = hq_debug_group_plan_emulate(static_cast<const hq_group_plan*>(gg.plans.at(0)), state_re_im);
+            int rc = emulateGroup(gg, 0, state_re_im);
             if (rc != HQ_OK) return rc;
         }
     return HQ_OK;

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cassert>
+#include <string>
 
 #include "evaluator.h"
 #include "logger.h"
@@ -25,6 +26,28 @@ std::vector<int> runnableGates(const std::vector<Gate>& gates, const std::vector
         if (g.controlQubit2 >= 0) qd |= qindex(1) << g.controlQubit2;
         bool ok = !(qn & (blockedAll | blockedNonDiag)) && !(qd & blockedAll);
         if (ok && !diag && !(tileSet >> g.targetQubit & 1)) ok = false;
+        if (ok) out.push_back(gi);
+        else { blockedAll |= qn; blockedNonDiag |= qd; }
+    }
+    return out;
+}
+
+// Same scan for a dense block: a gate may join only if ALL its qubits (controls and diagonal targets too) lie in
+// `qset` -- the block's matrix acts on nothing else (the reference's enableGlobal=false mode, src/compiler.cpp:265-278).
+std::vector<int> runnableDense(const std::vector<Gate>& gates, const std::vector<int>& order, qindex qset, int cap) {
+    std::vector<int> out;
+    qindex blockedAll = 0, blockedNonDiag = 0;
+    int seen = 0;
+    for (int gi : order) {
+        if (++seen > cap) break;
+        const Gate& g = gates[gi];
+        const bool diag = g.isDiagonal();
+        qindex qn = 0, qd = 0;
+        (diag ? qd : qn) |= qindex(1) << g.targetQubit;
+        if (g.controlQubit >= 0) qd |= qindex(1) << g.controlQubit;
+        if (g.controlQubit2 >= 0) qd |= qindex(1) << g.controlQubit2;
+        bool ok = !(qn & (blockedAll | blockedNonDiag)) && !(qd & blockedAll);
+        if (ok && ((qn | qd) & ~qset)) ok = false;
         if (ok) out.push_back(gi);
         else { blockedAll |= qn; blockedNonDiag |= qd; }
     }
@@ -70,6 +93,13 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
     tileBits = std::min(hq_group_tile_bits(), numLocal);
     pinnedBits = std::min(5, tileBits);
     if (const char* e = getenv("HQ_PINNED_BITS")) pinnedBits = std::max(hq_group_min_run_bits(), std::min(atoi(e), tileBits));
+    backendMode = 4;   // the reference's BACKEND numbering: 1 = group (tile kernel only), 3 = blas (dense only), 4 = mix
+    if (const char* e = getenv("HQ_BACKEND")) {
+        const std::string v = e;
+        backendMode = (v == "group" || v == "1") ? 1 : ((v == "blas" || v == "3") ? 3 : 4);
+    }
+    matLimit = 6;
+    if (const char* e = getenv("HQ_MAT")) matLimit = std::max(3, std::min(atoi(e), 6));
     overlapSlack = 1.0;
     if (const char* e = getenv("HQ_OVERLAP_SLACK")) overlapSlack = atof(e);
     enableOverlap = true;
@@ -123,6 +153,85 @@ std::vector<Compiler::Stage> Compiler::splitStages() const {
     return stages;
 }
 
+// ---- dense (TransMM-class) candidate ---------------------------------------------------------------------
+// One launch of the fused dense kernel = up to 8 matrices of <= 6 qubits each whose qubits, together with the three
+// lowest physical bits, fit one 12-bit tile.  Blocks are grown greedily from the frontier: repeatedly merge the qubits
+// of the gate that lets the block absorb the most additional gates.
+GateGroup Compiler::denseCandidate(const std::vector<Gate>& stageGates, const std::vector<int>& remaining0, const State& state,
+                                   int nLocal) const {
+    Evaluator* ev = Evaluator::getInstance();
+    GateGroup gg;
+    gg.backend = Backend::BLAS;
+    gg.state = state;
+    std::vector<int> remaining = remaining0;
+    const int lookahead = 512, tileCap = std::min(12, nLocal);
+    qindex tileQubits = 0;   // logical qubits whose physical bits the launch's tile must contain
+    for (int p = 0; p < std::min(3, nLocal); p++) tileQubits |= qindex(1) << state.layout[p];
+    auto qubitsOf = [](const Gate& g) {
+        qindex q = qindex(1) << g.targetQubit;
+        if (g.controlQubit >= 0) q |= qindex(1) << g.controlQubit;
+        if (g.controlQubit2 >= 0) q |= qindex(1) << g.controlQubit2;
+        return q;
+    };
+    double denseMs = 0;
+    while ((int)gg.blocks.size() < 8 && !remaining.empty()) {
+        // best block for every size cap; keep the one with the most gates per predicted millisecond
+        qindex bestSet = 0; std::vector<int> bestTake; double bestRate = 0; int bestM = 0;
+        for (int cap = 3; cap <= matLimit; cap++) {
+            qindex S = 0;
+            std::vector<int> cur;
+            while (true) {
+                qindex pickSet = 0; size_t pickCount = cur.size();
+                int scanned = 0;
+                for (int gi : remaining) {
+                    if (++scanned > 96) break;
+                    const qindex S2 = S | qubitsOf(stageGates[gi]);
+                    if (S2 == S || bitCount(S2) > cap) continue;
+                    if (bitCount(tileQubits | S2) > tileCap) continue;
+                    bool local = true;
+                    for (int q = 0; q < numQubits; q++) if ((S2 >> q & 1) && state.pos[q] >= nLocal) local = false;
+                    if (!local) continue;
+                    const size_t cnt = hyquas::runnableDense(stageGates, remaining, S2, lookahead).size();
+                    if (cnt > pickCount || (cnt == pickCount && pickSet && cnt > cur.size() && bitCount(S2) < bitCount(pickSet))) {
+                        pickSet = S2; pickCount = cnt;
+                    }
+                }
+                if (!pickSet) break;
+                S = pickSet;
+                cur = hyquas::runnableDense(stageGates, remaining, S, lookahead);
+            }
+            if (cur.empty()) continue;
+            const int m = std::max(3, bitCount(S));
+            const double rate = cur.size() / ev->denseMs30[m];
+            if (rate > bestRate * 1.0001) { bestRate = rate; bestSet = S; bestTake = cur; bestM = m; }
+        }
+        if (bestTake.empty()) break;
+        const double blockMs = ev->denseMs30[bestM];
+        // further blocks must pay for themselves: stop once the launch is compute-bound and the new block is slower per
+        // gate than what the launch already achieves
+        if (!gg.blocks.empty()) {
+            const double sweep = ev->sweepMs30();
+            const double before = std::max(sweep, denseMs), after = std::max(sweep, denseMs + blockMs);
+            if ((after - before) / bestTake.size() > before / gg.gates.size()) break;
+        }
+        DenseBlock blk;
+        blk.qubits = bestSet;
+        for (int gi : bestTake) { blk.gates.push_back(stageGates[gi]); gg.gates.push_back(stageGates[gi]); }
+        gg.blocks.push_back(std::move(blk));
+        gg.relatedQubits |= bestSet;
+        gg.matQubit = std::max(gg.matQubit, bestM);
+        tileQubits |= bestSet;
+        denseMs += blockMs;
+        std::vector<int> rest;
+        std::set_difference(remaining.begin(), remaining.end(), bestTake.begin(), bestTake.end(), std::back_inserter(rest));
+        remaining.swap(rest);
+    }
+    std::vector<int> ms;
+    for (auto& b : gg.blocks) ms.push_back(std::max(3, bitCount(b.qubits)));
+    gg.predictedMs = gg.blocks.empty() ? 0 : ev->perfDense(nLocal, ms);
+    return gg;
+}
+
 // ---- gate groups inside one stage ----------------------------------------------------------------------
 std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal) const {
     std::vector<GateGroup> groups;
@@ -158,9 +267,23 @@ std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, 
         gg.relatedQubits = tile;
         gg.state = state;
         for (int gi : take) gg.gates.push_back(stageGates[gi]);
-        std::vector<GateType> tys;
-        for (const Gate& g : gg.gates) tys.push_back(g.type);
-        gg.predictedMs = Evaluator::getInstance()->perfPerGate(nLocal, tys);
+        gg.predictedMs = Evaluator::getInstance()->perfPerGate(nLocal, gg.gates);
+        if (backendMode != 1 && nLocal >= 8) {
+            // hybrid choice (the reference's AdvanceCompiler::run, src/compiler.cpp:250-278): price a dense launch for
+            // the same frontier and keep whichever costs fewer predicted milliseconds per gate
+            GateGroup dense = denseCandidate(stageGates, remaining, state, nLocal);
+            const bool pick = !dense.gates.empty() &&
+                (backendMode == 3 || nLocal < 10 ||
+                 dense.predictedMs / dense.gates.size() < gg.predictedMs / gg.gates.size());
+            if (pick) {
+                gg = std::move(dense);
+                take.clear();
+                std::vector<int> ids;
+                for (auto& g : gg.gates) ids.push_back(g.gateID);
+                std::sort(ids.begin(), ids.end());
+                for (int gi : remaining) if (std::binary_search(ids.begin(), ids.end(), stageGates[gi].gateID)) take.push_back(gi);
+            }
+        }
         std::vector<int> rest;
         std::set_difference(remaining.begin(), remaining.end(), take.begin(), take.end(), std::back_inserter(rest));
         remaining.swap(rest);

@@ -23,10 +23,13 @@ public:
     int pinnedBits;    // lowest physical bits always kept in the tile (contiguous-run length of HBM accesses)
     int maxGroupGates; // cap on gates per group
     bool enableOverlap; // per-chunk groups under the exchange (reference: ENABLE_OVERLAP)
+    int backendMode;   // 1 = tile kernel only, 3 = dense kernel only, 4 = hybrid (reference: -DBACKEND=group|blas|mix)
+    int matLimit;      // largest dense block in qubits (reference: -DMAT, BLAS_MAT_LIMIT)
     double overlapSlack; // deferred work may take up to this multiple of the predicted exchange time
 private:
     struct Stage { std::vector<Gate> gates; qindex locals; };
     std::vector<Stage> splitStages() const;
+    GateGroup denseCandidate(const std::vector<Gate>& gates, const std::vector<int>& remaining, const State& state, int numLocal) const;
     std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal) const;
     int numQubits;
     int numLocal;
@@ -38,5 +41,6 @@ namespace hyquas {
 // which of `gates` (indices into it, in program order) can run now if exactly the qubits in `tileSet` may be
 // non-diagonal targets?  Gates that cannot run block later gates they do not commute with.
 std::vector<int> runnableGates(const std::vector<Gate>& gates, const std::vector<int>& order, qindex tileSet, int cap);
+std::vector<int> runnableDense(const std::vector<Gate>& gates, const std::vector<int>& order, qindex qset, int cap);
 hyquas::SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal);
 }

@@ -11,23 +11,27 @@ Evaluator* Evaluator::getInstance() {
 }
 
 Evaluator::Evaluator() {
-    // Defaults: B200, FP64.  In-register cost per gate class = FP64 issue slots per amplitude / (148 SMs x 64
-    // FP64 lanes x ~1.7 GHz sustained), expressed in ms per 2^30 amplitudes; refined by tools/calibrate.py.
-    hbmGBs = 5800.0;
+    // Defaults = this pool's B200, FP64, measured with tools/microbench.py at 2^30 amplitudes (profiles/r01_s4_microbench.json):
+    // a gate-group launch of G same-type gates takes  max(sweep, groupBaseMs30 + G * gate cost + extra rounds * roundMs30);
+    // a fused dense launch takes  max(sweep, denseBaseMs30 + sum of per-matrix costs).  tools/calibrate.py rewrites them
+    // from a fresh microbenchmark run ($HYQUAS_PARAM_FILE).
+    hbmGBs = 5940.0;        // one in-place sweep (16 B read + 16 B written per amplitude): 5.78 ms per 2^30
     launchMs = 0.01;
     nvlinkGBs = 700.0;
-    roundMs30 = 0.55;
-    const double slot = 1073741824.0 / (148.0 * 64.0 * 1.7e9) * 1e3;   // ms per FP64 slot per amplitude at 2^30
-    for (auto& g : gateNs) g = 4 * slot;
-    auto set = [&](GateType t, double slots) { gateNs[int(t)] = slots * slot; };
-    set(GateType::CCX, 0.3); set(GateType::CNOT, 0.5); set(GateType::X, 1.0);
-    set(GateType::CY, 1.0); set(GateType::Y, 2.0);
-    set(GateType::CZ, 0.6); set(GateType::Z, 1.2);
-    set(GateType::CRX, 2.2); set(GateType::CRY, 2.2); set(GateType::RX, 4.2); set(GateType::RY, 4.2);
-    set(GateType::CU1, 1.2); set(GateType::CRZ, 2.4); set(GateType::U1, 2.2); set(GateType::RZ, 4.2);
-    set(GateType::U2, 8.5); set(GateType::U3, 8.5); set(GateType::H, 4.2);
-    set(GateType::S, 2.2); set(GateType::SDG, 2.2); set(GateType::T, 2.2); set(GateType::TDG, 2.2);
-    for (int m = 0; m < 8; m++) denseMs30[m] = std::max(32.0 * 1073741824.0 / (hbmGBs * 1e9) * 1e3, 4.0 * (1 << m) * slot);
+    groupBaseMs30 = 1.9;
+    denseBaseMs30 = 0.6;
+    roundMs30 = 3.2;
+    for (auto& g : gateNs) g = 0.40;
+    auto set = [&](GateType t, double ms30) { gateNs[int(t)] = ms30; };
+    set(GateType::H, 0.35); set(GateType::RY, 0.37); set(GateType::RX, 0.50);
+    set(GateType::U2, 0.75); set(GateType::U3, 0.75);
+    set(GateType::T, 0.33); set(GateType::TDG, 0.33); set(GateType::S, 0.33); set(GateType::SDG, 0.33); set(GateType::U1, 0.33);
+    set(GateType::RZ, 0.45); set(GateType::Z, 0.20); set(GateType::X, 0.37); set(GateType::Y, 0.37);
+    set(GateType::CZ, 0.20); set(GateType::CU1, 0.27); set(GateType::CRZ, 0.35);
+    set(GateType::CNOT, 0.27); set(GateType::CY, 0.30); set(GateType::CCX, 0.20);
+    set(GateType::CRX, 0.45); set(GateType::CRY, 0.40);
+    const double dense[8] = {2.7, 2.7, 2.7, 2.7, 5.4, 9.7, 20.1, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
+    for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
 }
 
 void Evaluator::loadParam(int) {
@@ -47,6 +51,8 @@ void Evaluator::loadParam(int) {
         else if (key == "launch_ms") in >> launchMs;
         else if (key == "nvlink_gbs") in >> nvlinkGBs;
         else if (key == "round_ms30") in >> roundMs30;
+        else if (key == "group_base_ms30") in >> groupBaseMs30;
+        else if (key == "dense_base_ms30") in >> denseBaseMs30;
         else if (key == "gate") { int i; double v; in >> i >> v; if (i >= 0 && i < 32) gateNs[i] = v; }
         else if (key == "dense") { int i; double v; in >> i >> v; if (i >= 0 && i < 8) denseMs30[i] = v; }
     }
@@ -54,18 +60,33 @@ void Evaluator::loadParam(int) {
 
 double Evaluator::perfPerGate(int numQubits, const std::vector<GateType>& types) {
     loadParam(numQubits);
-    const double scale = std::ldexp(1.0, numQubits - 30);
-    double compute = 0;
+    double compute = groupBaseMs30;
     for (GateType t : types) compute += gateNs[int(t) & 31];
-    compute += roundMs30 * (1 + types.size() / 24.0);
-    const double sweep = 32.0 * 1073741824.0 / (hbmGBs * 1e9) * 1e3;
-    return launchMs + scale * std::max(sweep, compute);
+    return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
 }
 
-double Evaluator::perfPerGate(int numQubits, const GateGroup* gg) {
-    std::vector<GateType> tys;
-    for (const Gate& g : gg->gates) tys.push_back(g.type);
-    return perfPerGate(numQubits, tys);
+// With the gates at hand the number of register rounds can be bounded from below: a round holds 4 register qubits.
+double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
+    loadParam(numQubits);
+    double compute = groupBaseMs30;
+    qindex targets = 0;
+    for (const Gate& g : gates) {
+        compute += gateNs[int(g.type) & 31];
+        if (!g.isDiagonal()) targets |= qindex(1) << g.targetQubit;
+    }
+    const int rounds = std::max(1, (bitCount(targets) + 3) / 4);
+    compute += roundMs30 * (rounds - 1);
+    return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
+}
+
+double Evaluator::perfPerGate(int numQubits, const GateGroup* gg) { return perfPerGate(numQubits, gg->gates); }
+
+double Evaluator::perfDense(int numQubits, const std::vector<int>& ms) {
+    loadParam(numQubits);
+    double compute = 0;
+    compute = denseBaseMs30;
+    for (int m : ms) compute += denseMs30[std::min(std::max(m, 0), 7)];
+    return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
 }
 
 double Evaluator::perfSwap(int numQubits, int k) {

@@ -18,8 +18,12 @@ public:
     // predicted milliseconds for one gate-group launch over 2^numQubits local amplitudes
     double perfPerGate(int numQubits, const GateGroup* gg);
     double perfPerGate(int numQubits, const std::vector<GateType>& types);
+    double perfPerGate(int numQubits, const std::vector<Gate>& gates);
     // predicted milliseconds for one fused dense (TransMM) launch with a 2^blasSize x 2^blasSize matrix
     double perfBLAS(int numQubits, int blasSize);
+    // one fused dense launch applying several matrices (qubit counts in `ms`) in a single sweep
+    double perfDense(int numQubits, const std::vector<int>& ms);
+    double sweepMs30() const { return 32.0 * 1073741824.0 / (hbmGBs * 1e9) * 1e3; }
     // predicted milliseconds for swapping k local bits with k global bits (NVLink bytes / measured bandwidth)
     double perfSwap(int numQubits, int k);
     double nvlinkGBs;                       // per-direction bandwidth of one GPU during the exchange
@@ -28,6 +32,8 @@ public:
     // model constants (public so that the calibration tool and tests can read/write them)
     double hbmGBs;                          // achieved sweep bandwidth of the gate-group kernel (read+write)
     double gateNs[32];                      // per-gate cost per 2^30 amplitudes in ms, indexed by GateType
+    double groupBaseMs30;                   // fixed part of a gate-group launch that does not overlap the sweep
+    double denseBaseMs30;                   // same for the fused dense kernel
     double roundMs30;                       // cost of one extra register round per 2^30 amplitudes, ms
     double denseMs30[8];                    // fused dense kernel, per 2^30 amplitudes, indexed by matrix qubits
     double launchMs;                        // fixed per-launch overhead

@@ -1,6 +1,8 @@
 #include "executor.h"
 
+#include <algorithm>
 #include <cassert>
+#include <complex>
 #include <cstring>
 
 #include "logger.h"
@@ -75,6 +77,76 @@ static void preparePerGate(GateGroup& gg, int numQubits, int numLocal, int numCh
     }
 }
 
+// Dense matrix of one block for the sub-state whose high index bits equal `high`: U = G_last ... G_1 acting on the
+// block's qubits (matrix bit i = i-th lowest physical position).  Role of GateGroup::initCPUMatrix
+// (src/schedule.cpp:578-702); gates with global controls/targets are resolved per shard by lowerGate.
+static std::vector<double> buildDenseMatrix(const DenseBlock& blk, const State& state, int numLocal, qindex high,
+                                            const std::vector<int>& positions) {
+    const int m = (int)positions.size(), K = 1 << m;
+    std::vector<std::complex<double>> U((size_t)K * K, 0.0);   // column-major: U[row + col * K]
+    for (int i = 0; i < K; i++) U[(size_t)i + (size_t)i * K] = 1.0;
+    int bitOf[64];
+    for (int i = 0; i < 64; i++) bitOf[i] = -1;
+    for (int i = 0; i < m; i++) bitOf[positions[i]] = i;
+    for (const Gate& g : blk.gates) {
+        hq_gate k;
+        if (!Executor::lowerGate(g, state, numLocal, high, k)) continue;
+        const std::complex<double> m00(k.mat[0], k.mat[1]), m01(k.mat[2], k.mat[3]), m10(k.mat[4], k.mat[5]), m11(k.mat[6], k.mat[7]);
+        int cmask = 0;
+        for (int c : {k.control, k.control2}) {
+            if (c < 0) continue;
+            if (bitOf[c] < 0) UNREACHABLE()
+            cmask |= 1 << bitOf[c];
+        }
+        if (k.target < 0) {   // scalar
+            for (auto& v : U) v *= m00;
+            continue;
+        }
+        if (bitOf[k.target] < 0) UNREACHABLE()
+        const int tb = 1 << bitOf[k.target];
+        #pragma omp parallel for if (K >= 32)
+        for (int col = 0; col < K; col++) {
+            std::complex<double>* v = &U[(size_t)col * K];
+            for (int lo = 0; lo < K; lo++) {
+                if ((lo & tb) || (lo & cmask) != cmask) continue;
+                const std::complex<double> a = v[lo], b = v[lo | tb];
+                v[lo] = m00 * a + m01 * b;
+                v[lo | tb] = m10 * a + m11 * b;
+            }
+        }
+    }
+    std::vector<double> out((size_t)K * K * 2);
+    for (size_t i = 0; i < U.size(); i++) { out[2 * i] = U[i].real(); out[2 * i + 1] = U[i].imag(); }
+    return out;
+}
+
+static void prepareDense(GateGroup& gg, int numQubits, int numLocal, int numChunks) {
+    const qindex rank = MyMPI::rank;
+    for (int chunk = 0; chunk < numChunks; chunk++) {
+        const qindex high = numChunks > 1 ? ((rank * numChunks) | chunk) : rank;
+        std::vector<int> mList, qpos;
+        std::vector<double> allU;
+        for (const DenseBlock& blk : gg.blocks) {
+            std::vector<int> positions;
+            for (int q = 0; q < numQubits; q++) if (blk.qubits >> q & 1) positions.push_back(gg.state.pos[q]);
+            std::sort(positions.begin(), positions.end());
+            std::vector<double> U = buildDenseMatrix(blk, gg.state, numLocal, high, positions);
+            mList.push_back((int)positions.size());
+            qpos.insert(qpos.end(), positions.begin(), positions.end());
+            allU.insert(allU.end(), U.begin(), U.end());
+        }
+        hq_dense_plan* plan = nullptr;
+        checkHq(hq_dense_plan_create(numLocal, (int)mList.size(), mList.data(), qpos.data(), allU.data(), &plan));
+        gg.plans.push_back(plan);
+    }
+}
+
+static void prepareGroup(GateGroup& gg, int numQubits, int numLocal, int numChunks) {
+    if (!gg.plans.empty()) return;
+    if (gg.backend == Backend::BLAS) prepareDense(gg, numQubits, numLocal, numChunks);
+    else preparePerGate(gg, numQubits, numLocal, numChunks);
+}
+
 void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
     const int L = numQubits - MyGlobalVars::bit;
     for (auto& lg : schedule.localGroups) {
@@ -84,8 +156,8 @@ void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
             checkHq(hq_swap_plan_create(L, k, lg.swap.localBit.data(), lg.swap.globalBit.data(), &sp));
             lg.swapPlan = sp;
         }
-        for (auto& gg : lg.overlapGroups) if (gg.plans.empty()) preparePerGate(gg, numQubits, L - k, 1 << k);
-        for (auto& gg : lg.fullGroups) if (gg.plans.empty()) preparePerGate(gg, numQubits, L, 1);
+        for (auto& gg : lg.overlapGroups) prepareGroup(gg, numQubits, L - k, 1 << k);
+        for (auto& gg : lg.fullGroups) prepareGroup(gg, numQubits, L, 1);
     }
 }
 
@@ -95,7 +167,10 @@ void Executor::release(Schedule& schedule) {
         lg.swapPlan = nullptr;
         for (auto* groups : {&lg.overlapGroups, &lg.fullGroups})
             for (auto& gg : *groups) {
-                for (void* p : gg.plans) hq_group_plan_destroy(static_cast<hq_group_plan*>(p));
+                for (void* p : gg.plans) {
+                    if (gg.backend == Backend::BLAS) hq_dense_plan_destroy(static_cast<hq_dense_plan*>(p));
+                    else hq_group_plan_destroy(static_cast<hq_group_plan*>(p));
+                }
                 gg.plans.clear();
             }
     }
@@ -104,14 +179,18 @@ void Executor::release(Schedule& schedule) {
 void Executor::applyGateGroup(GateGroup& gg, int chunk) {
     const int L = numQubits - MyGlobalVars::bit;
     if (perGroupMs) checkHq(hq_timer_start());
+    auto launch = [&](void* plan, qComplex* base) {
+        if (gg.backend == Backend::BLAS) checkHq(hq_dense_plan_launch(static_cast<hq_dense_plan*>(plan), base, 0))
+        else checkHq(hq_group_plan_launch(static_cast<hq_group_plan*>(plan), base, 0))
+    };
     if (chunk < 0) {
-        checkHq(hq_group_plan_launch(static_cast<hq_group_plan*>(gg.plans[0]), deviceStateVec[0], 0));
+        launch(gg.plans[0], deviceStateVec[0]);
     } else {
         const int nChunks = (int)gg.plans.size();
         int k = 0;
         while ((1 << k) < nChunks) k++;
         qComplex* base = deviceStateVec[0] + ((qindex)chunk << (L - k));
-        checkHq(hq_group_plan_launch(static_cast<hq_group_plan*>(gg.plans[chunk]), base, 0));
+        launch(gg.plans[chunk], base);
     }
     if (perGroupMs) {
         float ms = 0;

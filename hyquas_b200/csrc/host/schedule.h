@@ -44,12 +44,19 @@ struct SwapPlan {
 };
 }  // namespace hyquas
 
+// One dense matrix of a BLAS-backend group: the gates it fuses and the logical qubits it spans.
+struct DenseBlock {
+    qindex qubits = 0;
+    std::vector<Gate> gates;
+};
+
 struct GateGroup {
     std::vector<Gate> gates;
     qindex relatedQubits = 0;     // logical qubits the kernel keeps in its tile / matrix
     Backend backend = Backend::PerGate;
     State state;                  // layout while (and after) this group runs
-    int matQubit = 0;             // BLAS: number of matrix qubits
+    int matQubit = 0;             // BLAS: matrix qubits of the largest block
+    std::vector<DenseBlock> blocks;   // BLAS: the dense matrices applied, in order, by this one launch
     double predictedMs = 0;       // evaluator's estimate
 
     // device side, filled by Circuit::compile() for this process

@@ -85,6 +85,19 @@ int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes);   /* size 
 int hq_group_plan_destroy(hq_group_plan* plan);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 
+/* ---- fused dense-matrix kernel (replaces the TransMM path: cuttExecute + cublasZgemm in Executor::applyBlasGroup,
+ *      src/executor.cpp:533-575, and the device upload of GateGroup::initGPUMatrix, src/schedule.cpp:704-721).
+ *      One in-place sweep applies nmat dense matrices in order; matrix i acts on m_list[i] qubits whose physical
+ *      local bit positions are the next m_list[i] entries of qubit_pos (entry b = bit b of the row/column index);
+ *      U is column-major, interleaved (re, im), 2^m x 2^m, like the A operand of the reference's Zgemm call.
+ *      All matrices of one plan must fit in one tile: their qubits together with physical bits 0..2 span <= 12 bits. */
+typedef struct hq_dense_plan hq_dense_plan;
+int hq_dense_plan_create(int L, int nmat, const int* m_list, const int* qubit_pos, const double* u_colmajor, hq_dense_plan** plan);
+int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int on_comm_stream);
+int hq_dense_plan_info(const hq_dense_plan* plan, int* tile_bits, int* smem_bytes, int* grid, double* flops_per_amp, int* table_bytes);
+int hq_dense_plan_destroy(hq_dense_plan* plan);
+int hq_dense_apply(void* state, int L, int m, const int* qubit_pos, const double* u_colmajor);   /* create+launch+destroy */
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink (replaces the NCCL bootstrap of MyGlobalVars::init,
  *      src/utils.cpp:46-58, and Executor::transpose + all2all + sliceBarrier, src/executor.cpp:59-179,650-659).
  *      The swap trades the top k local bits with k global bits IN PLACE: the local state is 2^k contiguous chunks;

@@ -38,6 +38,7 @@ int hq_circuit_execute(hq_circuit* c, int* time_us, double* device_ms, float* pe
 int hq_circuit_norm2(hq_circuit* c, double* out);
 int hq_circuit_io_bytes(const hq_circuit* c, size_t* h2d_plan_bytes, size_t* d2h_dump_bytes);
 int hq_circuit_schedule_info(const hq_circuit* c, int* stages, int* groups, int* gates_in_groups);
+int hq_circuit_group_info(const hq_circuit* c, int index, int* backend, int* ngates, double* predicted_ms, int* launches, int* nblocks);
 int hq_circuit_dump(hq_circuit* c, char* buf, size_t cap, size_t* needed);              /* printState text */
 int hq_circuit_amplitudes(hq_circuit* c, double* out_re_im); /* all 2^n amplitudes, logical order (small n) */
 int hq_circuit_local_shard(hq_circuit* c, double* out_re_im);  /* this process' 2^(n-g) amplitudes, physical order */

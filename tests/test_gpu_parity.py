@@ -155,3 +155,55 @@ def test_dump_scan_and_fetch(gpu_runtime):
     check(lib.hq_amp_fetch(dev, 40000, one))
     assert (one[0], one[1]) == (0.0, 0.8)
     check(lib.hq_state_free(dev))
+
+
+# ---- fused dense-matrix (TransMM-class) kernel -----------------------------------------------------------------------
+def _apply_dense_np(state, n, qubits, U):
+    m = len(qubits)
+    psi = state.reshape([2] * n)
+    axes = [n - 1 - q for q in reversed(qubits)]
+    psi = np.moveaxis(psi, axes, range(m))
+    shp = psi.shape
+    psi = (U @ psi.reshape(1 << m, -1)).reshape(shp)
+    return np.ascontiguousarray(np.moveaxis(psi, range(m), axes)).reshape(-1)
+
+
+def _pack_u(mats):
+    out = []
+    for U in mats:
+        cm = np.asarray(U).T.reshape(-1)
+        out.append(np.stack([cm.real, cm.imag], axis=1).reshape(-1))
+    return np.ascontiguousarray(np.concatenate(out))
+
+
+@pytest.mark.parametrize("n,groups", [
+    (12, [[0, 1, 2]]), (14, [[3, 7, 11]]), (16, [[5, 9, 10, 12]]), (18, [[0, 4, 8, 12, 17]]), (18, [[2, 3, 5, 7, 11, 13]]),
+    (15, [[6]]), (15, [[1, 9]]), (20, [[14, 15, 16, 17, 18, 19]]), (20, [[3, 6, 9, 12]]),
+    (20, [[4, 5, 6], [6, 7, 8, 9], [0, 15]]), (17, [[10, 11, 12, 13], [3, 10, 11, 12, 13]]), (13, [[4, 5, 6, 7, 8, 9], [0, 1, 2, 3, 10, 11]]),
+    (22, [[0, 1, 2, 3, 4, 5]]), (22, [[16, 17, 18, 19, 20, 21], [3, 4, 5, 16]]),
+])
+def test_dense_kernel_vs_numpy(gpu_runtime, n, groups):
+    """hq_dense_plan_launch (DMMA kernel) == numpy U @ x on the chosen qubits, random unitary, random state."""
+    from hyquas_b200._lib import check, lib
+    rng = np.random.default_rng(n * 31 + len(groups))
+    st = _random_state(n, n)
+    mats = []
+    for q in groups:
+        a = rng.standard_normal((1 << len(q), 1 << len(q))) + 1j * rng.standard_normal((1 << len(q), 1 << len(q)))
+        mats.append(np.linalg.qr(a)[0])
+    want = st.copy()
+    for q, U in zip(groups, mats):
+        want = _apply_dense_np(want, n, q, U)
+    m_list = (ctypes.c_int * len(groups))(*[len(q) for q in groups])
+    flat = [b for q in groups for b in q]
+    u = _pack_u(mats)
+    plan, dev = ctypes.c_void_p(), ctypes.c_void_p()
+    check(lib.hq_dense_plan_create(n, len(groups), m_list, (ctypes.c_int * len(flat))(*flat), u.ctypes.data, ctypes.byref(plan)))
+    check(lib.hq_state_alloc(n, ctypes.byref(dev)))
+    check(lib.hq_state_upload(dev, n, 0, 1 << n, st.ctypes.data))
+    check(lib.hq_dense_plan_launch(plan, dev, 0))
+    got = np.empty_like(st)
+    check(lib.hq_state_download(dev, n, 0, 1 << n, got.ctypes.data))
+    check(lib.hq_state_free(dev))
+    lib.hq_dense_plan_destroy(plan)
+    assert np.max(np.abs(got - want)) <= 1e-13

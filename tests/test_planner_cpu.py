@@ -105,11 +105,41 @@ def test_compiled_random_circuits(n, seed):
     assert np.max(np.abs(got - O.simulate(n, gates))) < 1e-12
 
 
-def test_schedule_shapes_of_reference_benchmarks():
-    """Sweeps per circuit stay in the range the reference's own partitioner produces."""
+def test_schedule_shapes_of_reference_benchmarks(monkeypatch):
+    """Sweeps per circuit stay in the range the reference's own partitioner produces, tile backend."""
+    monkeypatch.setenv("HQ_BACKEND", "group")
     api.init_host_only(1, 0)
     for name, max_groups in [("qft_28", 5), ("bv_28", 5), ("hidden_shift_28", 5), ("supremacy_30", 14)]:
         c = api.Circuit.from_qasm(C.generate(name))
         info = c.plan_only()
         assert info["stages"] == 1 and 1 <= info["groups"] <= max_groups, (name, info)
         c.close()
+
+
+@pytest.mark.parametrize("mode", ["group", "blas", "mix"])
+@pytest.mark.parametrize("name", ["supremacy_16", "quantum_volume_14", "qaoa_16", "adder_16", "qft_14"])
+def test_backends_agree_with_oracle(monkeypatch, mode, name):
+    """-DBACKEND=group|blas|mix of the reference (CMakeLists.txt:31-45) as a run-time knob: same amplitudes from the tile
+    kernel's plan, the dense kernel's plan, and the evaluator-driven mixture."""
+    monkeypatch.setenv("HQ_BACKEND", mode)
+    text = C.generate(name)
+    n, got, info = emulate_circuit(text)
+    _, gates = O.parse_qasm(text)
+    assert info["gates"] == len(gates)
+    assert np.max(np.abs(got - O.simulate(n, gates))) < 1e-12
+
+
+def test_hybrid_prefers_dense_for_quantum_volume(monkeypatch):
+    """The evaluator prices u3-heavy SU(4) blocks cheaper as fused dense matrices; cheap-gate circuits such as qft stay on
+    the tile kernel."""
+    api.init_host_only(1, 0)
+    monkeypatch.setenv("HQ_BACKEND", "mix")
+    c = api.Circuit.from_qasm(C.generate("quantum_volume_24"))
+    c.compile()
+    kinds = [g["backend"] for g in c.groups()]
+    assert kinds.count("dense") > len(kinds) // 2
+    c.close()
+    c = api.Circuit.from_qasm(C.generate("qft_24"))
+    c.compile()
+    assert all(g["backend"] == "tile" for g in c.groups())
+    c.close()

@@ -92,6 +92,44 @@ def main():
         print(f"{name:16s} gates={count:4d} groups={len(per)} total={min(ms, ms2):8.3f} ms  per-group={['%.2f' % x for x in per]}",
               flush=True)
         c.close()
+    # fused dense kernel: one or several random unitaries on m qubits, 2^n amplitudes
+    import numpy as np
+    rng = np.random.default_rng(5)
+    st = ctypes.c_void_p()
+    check(lib.hq_state_alloc(n, ctypes.byref(st)))
+    check(lib.hq_state_init(st, n, 1))
+    res["dense"] = {}
+    dense_cases = {"m3_low": [[0, 1, 2]], "m3_high": [[20, 21, 22]], "m4_low": [[0, 1, 2, 3]], "m4_high": [[20, 21, 22, 23]],
+                   "m5_low": [[0, 1, 2, 3, 4]], "m5_high": [[20, 21, 22, 23, 24]], "m6_low": [[0, 1, 2, 3, 4, 5]],
+                   "m6_high": [[20, 21, 22, 23, 24, 25]], "m4_mixed": [[1, 9, 17, 25]],
+                   "m4x2": [[3, 4, 5, 6], [7, 8, 9, 10]], "m4x3": [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11]], "m3x3_high": [[20, 21, 22], [23, 24, 25], [26, 27, 28]],
+                   "m3x2": [[3, 4, 5], [6, 7, 8]], "m5x2": [[0, 1, 2, 3, 4], [5, 6, 7, 8, 9]], "m3x8": [[3 + (i % 3) * 3 + j for j in range(3)] for i in range(8)],
+                   "m3x3": [[3, 4, 5], [6, 7, 8], [9, 10, 11]], "m2x4": [[3, 4], [5, 6], [7, 8], [9, 10]]}
+    for name, groups in dense_cases.items():
+        mats = []
+        for q in groups:
+            a = rng.standard_normal((1 << len(q), 1 << len(q))) + 1j * rng.standard_normal((1 << len(q), 1 << len(q)))
+            U = np.linalg.qr(a)[0]
+            cm = U.T.reshape(-1)
+            mats.append(np.stack([cm.real, cm.imag], axis=1).reshape(-1))
+        u = np.ascontiguousarray(np.concatenate(mats))
+        flat = [b for q in groups for b in q]
+        plan = ctypes.c_void_p()
+        check(lib.hq_dense_plan_create(n, len(groups), (ctypes.c_int * len(groups))(*[len(q) for q in groups]),
+                                       (ctypes.c_int * len(flat))(*flat), u.ctypes.data, ctypes.byref(plan)))
+        best = 1e9
+        for _ in range(4):
+            check(lib.hq_timer_start())
+            check(lib.hq_dense_plan_launch(plan, st, 0))
+            ms = ctypes.c_float()
+            check(lib.hq_timer_stop_ms(ms))
+            best = min(best, ms.value)
+        fl = ctypes.c_double()
+        check(lib.hq_dense_plan_info(plan, None, None, None, fl, None))
+        lib.hq_dense_plan_destroy(plan)
+        res["dense"][name] = {"ms": best, "gbs": 32.0 * (1 << n) / best / 1e6, "tflops": fl.value * (1 << n) / best / 1e9}
+        print(f"dense {name:10s} {best:8.3f} ms  {res['dense'][name]['gbs']:7.0f} GB/s  {res['dense'][name]['tflops']:6.2f} TFLOP/s", flush=True)
+    check(lib.hq_state_free(st))
     if args.out:
         json.dump(res, open(args.out, "w"), indent=1)
 
