@@ -267,15 +267,23 @@ def run_ours(args, world, rank, local_rank):
     # ---- e2e: the public API from host inputs (QASM text) to host outputs (amplitude dump) -----------------
     e2e_steps = max(1, min(args.steps, 3))
     h2d = d2h = 0
+    parts = {"parse": 0.0, "compile_and_plan_upload": 0.0, "run_alloc_init_execute_dump_readback": 0.0, "free": 0.0}
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         ce = api.Circuit.from_qasm(text)
+        tb = time.perf_counter()
         ce.compile()
-        ce.run(copy_back=False, destroy=True)
+        tc = time.perf_counter()
+        ce.run(copy_back=False, destroy=False)
         dump = ce.dump()
+        td = time.perf_counter()
         h2d, d2h = ce.io_bytes()
         ce.close()
+        te = time.perf_counter()
+        for k, v in zip(parts, (tb - ta, tc - tb, td - tc, te - td)):
+            parts[k] += v * 1e3 / e2e_steps
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
@@ -284,6 +292,7 @@ def run_ours(args, world, rank, local_rank):
         e2e_s = float(t.item())
     e2e = {"value": bytes_per_step / e2e_s / 1e12, "unit": "TB/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "breakdown_ms": {k: round(v, 2) for k, v in parts.items()},
            "path": "QASM text -> hq_circuit_from_qasm -> compile -> run(alloc, init, execute) -> dump"}
     api.logger_flush() if False else None
 

@@ -86,16 +86,26 @@ __device__ __forceinline__ void dense_block(double2* tile, const double2* __rest
         double2 x[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t) x[t] = tile[krow ^ ncol[t]];
+        // Two passes so that consecutive MMAs never hit the same accumulator back to back (asm volatile keeps this order):
+        // first the Re(U) products of every (row tile, column tile), then the Im(U) products.
+        double2 u[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) u[r] = ufrag[(r * K4 + k4) * 32 + lane];
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
-            const double2 u = ufrag[(r * K4 + k4) * 32 + lane];
-            const double nui = -u.y;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                dmma(accr[r][t][0], accr[r][t][1], u.x, x[t].x);
+                dmma(accr[r][t][0], accr[r][t][1], u[r].x, x[t].x);
+                dmma(acci[r][t][0], acci[r][t][1], u[r].x, x[t].y);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const double nui = -u[r].y;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
                 dmma(accr[r][t][0], accr[r][t][1], nui, x[t].y);
-                dmma(acci[r][t][0], acci[r][t][1], u.x, x[t].y);
-                dmma(acci[r][t][0], acci[r][t][1], u.y, x[t].x);
+                dmma(acci[r][t][0], acci[r][t][1], u[r].y, x[t].x);
             }
         }
     }
@@ -114,7 +124,10 @@ __device__ __forceinline__ void dense_block(double2* tile, const double2* __rest
     }
 }
 
-__global__ void __launch_bounds__(DENSE_THREADS) dense_kernel(const __grid_constant__ DenseParams P) {
+// MAXM = 4: every matrix of the launch has <= 4 qubits (16 accumulator doubles per thread, 3 CTAs per SM);
+// MAXM = 6: general (32 accumulator doubles, 2 CTAs per SM).
+template <int MAXM>
+__global__ void __launch_bounds__(DENSE_THREADS, MAXM <= 4 ? 3 : 2) dense_kernel(const __grid_constant__ DenseParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int TILE = 1 << P.Kt;
     double2* tile = reinterpret_cast<double2*>(smem_raw);
@@ -154,11 +167,16 @@ __global__ void __launch_bounds__(DENSE_THREADS) dense_kernel(const __grid_const
             const uint16_t* swk = tab_s + d.tab_off;
             const uint16_t* swn = swk + (1 << d.m);
             for (int nb = warp; nb < d.nblocks; nb += DENSE_THREADS / 32) {
-                switch (d.m) {
-                    case 3: dense_block<1, 4>(tile, uf, swk, swn, nb * 32, lane); break;
-                    case 4: dense_block<2, 4>(tile, uf, swk, swn, nb * 32, lane); break;
-                    case 5: dense_block<4, 2>(tile, uf, swk, swn, nb * 16, lane); break;
-                    default: dense_block<8, 1>(tile, uf, swk, swn, nb * 8, lane); break;
+                if (MAXM <= 4) {
+                    if (d.m == 3) dense_block<1, 4>(tile, uf, swk, swn, nb * 32, lane);
+                    else dense_block<2, 2>(tile, uf, swk, swn, nb * 16, lane);
+                } else {
+                    switch (d.m) {
+                        case 3: dense_block<1, 4>(tile, uf, swk, swn, nb * 32, lane); break;
+                        case 4: dense_block<2, 2>(tile, uf, swk, swn, nb * 16, lane); break;
+                        case 5: dense_block<4, 2>(tile, uf, swk, swn, nb * 16, lane); break;
+                        default: dense_block<8, 1>(tile, uf, swk, swn, nb * 8, lane); break;
+                    }
                 }
             }
             __syncthreads();
@@ -319,7 +337,7 @@ extern "C" int hq_dense_plan_create(int L, int nmat, const int* m_list, const in
         d.u_off = (uint32_t)ufrag.size();
         d.tab_off = (uint32_t)tables.size();
         const int RT = K / 8, K4 = K / 4;
-        const int NT = me <= 4 ? 4 : (me == 5 ? 2 : 1);
+        const int NT = me <= 3 ? 4 : (me <= 5 ? 2 : 1);
         d.nblocks = (1 << (Kt - me)) / (8 * NT);
         HQ_REQUIRE(d.nblocks >= 1, "tile too small for this matrix");
         for (int r = 0; r < RT; ++r)
@@ -398,15 +416,19 @@ extern "C" int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int 
     HQ_REQUIRE(rt().ready && plan->dev_blob, "dense plan was created without a bound GPU (call hq_init first)");
     static bool attr_set = false;
     if (!attr_set) {
-        HQ_CUDA(cudaFuncSetAttribute(dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    int maxm = 0;
+    for (int i = 0; i < plan->p.nmat; ++i) maxm = std::max(maxm, plan->p.mats[i].m);
+    auto kern = maxm <= 4 ? dense_kernel<4> : dense_kernel<6>;
     int nb = 0;
-    HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dense_kernel, DENSE_THREADS, plan->smem));
+    HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, DENSE_THREADS, plan->smem));
     DenseParams p = plan->p;
     p.state = static_cast<double2*>(state);
     plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)rt().sm_count * std::max(1, nb));
-    dense_kernel<<<plan->grid, DENSE_THREADS, plan->smem, on_comm_stream ? rt().comm : rt().compute>>>(p);
+    kern<<<plan->grid, DENSE_THREADS, plan->smem, on_comm_stream ? rt().comm : rt().compute>>>(p);
     HQ_CUDA(cudaGetLastError());
     return HQ_OK;
 }

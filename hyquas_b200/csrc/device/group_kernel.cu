@@ -449,6 +449,8 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
             tb[(size_t)(2 * r + 1) * NT + t] = (uint16_t)swz(j);
             gt[(size_t)r * NT + t] = pdep64(j, tile_mask);
         }
+        for (DevOp& o : body)   // body index for the kernel's single indexed branch
+            if (o.code < CODE_DIAG_T) o.flags |= (uint32_t)HQ_OP_BODY_INDEX[o.code] << 8;
         d.op_begin = (int)dops.size();
         if (!run.empty()) {   // the run commutes with every other op of the round (it touches no register bit)
             DevOp hdr{};

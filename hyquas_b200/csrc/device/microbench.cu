@@ -66,15 +66,24 @@ static int time_ms(cudaStream_t s, float* ms, const std::function<void()>& fn) {
 using namespace hq;
 
 // kind 0: FP64 FMA (CUDA cores), kind 1: FP64 tensor cores (mma.sync m8n8k4).  Reports dense TFLOP/s.
+// kind 10+w: DMMA with only w warps (of 8 independent accumulators) resident per SM -- how many warps the dense kernel
+// needs in its compute phase to keep the FP64 tensor pipe busy.
 extern "C" int hq_microbench_fp64(int kind, double* tflops) {
-    HQ_REQUIRE(rt().ready && tflops && (kind == 0 || kind == 1), "bad arguments to hq_microbench_fp64");
+    HQ_REQUIRE(rt().ready && tflops && (kind == 0 || kind == 1 || (kind > 10 && kind <= 74)), "bad arguments to hq_microbench_fp64");
     double* d = nullptr;
     HQ_CUDA(cudaMalloc(&d, 64));
-    const int iters = 20000, block = 256, grid = rt().sm_count * 8;
+    int iters = 20000, block = 256, grid = rt().sm_count * 8;
+    if (kind > 10) {   // one CTA per SM with (kind - 10) warps; extra dynamic smem keeps a second CTA off the SM
+        block = (kind - 10) * 32;
+        if (block > 1024) { grid = rt().sm_count * 2; block /= 2; }
+        else grid = rt().sm_count;
+    }
+    if (kind > 10) HQ_CUDA(cudaFuncSetAttribute(dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     float ms = 0;
     int rc = time_ms(rt().compute, &ms, [&] {
         if (kind == 0) dfma_kernel<<<grid, block, 0, rt().compute>>>(d, iters, 1.0000001, 1e-9);
-        else dmma_kernel<<<grid, block, 0, rt().compute>>>(d, iters, 1.0000001, 1e-9);
+        else if (kind == 1) dmma_kernel<<<grid, block, 0, rt().compute>>>(d, iters, 1.0000001, 1e-9);
+        else dmma_kernel<<<grid, block, 120 * 1024, rt().compute>>>(d, iters, 1.0000001, 1e-9);
     });
     cudaFree(d);
     if (rc != HQ_OK) return rc;

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cassert>
 #include <string>
+#include <unordered_map>
 
 #include "evaluator.h"
 #include "logger.h"
@@ -175,36 +176,54 @@ GateGroup Compiler::denseCandidate(const std::vector<Gate>& stageGates, const st
     };
     double denseMs = 0;
     while ((int)gg.blocks.size() < 8 && !remaining.empty()) {
-        // best block for every size cap; keep the one with the most gates per predicted millisecond
+        // best block for every size cap; keep the one with the most gates per predicted millisecond.  The same qubit
+        // sets come up again and again across caps and growth steps: their gate counts are memoised.
         qindex bestSet = 0; std::vector<int> bestTake; double bestRate = 0; int bestM = 0;
+        std::unordered_map<qindex, int> memo;
+        auto countFor = [&](qindex S2) {
+            auto it = memo.find(S2);
+            if (it != memo.end()) return it->second;
+            int cnt = -1;
+            if (bitCount(tileQubits | S2) <= tileCap) {
+                bool local = true;
+                for (int q = 0; q < numQubits; q++) if ((S2 >> q & 1) && state.pos[q] >= nLocal) local = false;
+                if (local) cnt = (int)hyquas::runnableDense(stageGates, remaining, S2, lookahead).size();
+            }
+            memo.emplace(S2, cnt);
+            return cnt;
+        };
+        std::vector<qindex> frontier;   // distinct qubit sets of the first gates
+        {
+            int scanned = 0;
+            for (int gi : remaining) {
+                if (++scanned > 96) break;
+                const qindex q = qubitsOf(stageGates[gi]);
+                if (std::find(frontier.begin(), frontier.end(), q) == frontier.end()) frontier.push_back(q);
+            }
+        }
         for (int cap = 3; cap <= matLimit; cap++) {
             qindex S = 0;
-            std::vector<int> cur;
+            int curCount = 0;
             while (true) {
-                qindex pickSet = 0; size_t pickCount = cur.size();
-                int scanned = 0;
-                for (int gi : remaining) {
-                    if (++scanned > 96) break;
-                    const qindex S2 = S | qubitsOf(stageGates[gi]);
+                qindex pickSet = 0; int pickCount = curCount;
+                for (qindex fq : frontier) {
+                    const qindex S2 = S | fq;
                     if (S2 == S || bitCount(S2) > cap) continue;
-                    if (bitCount(tileQubits | S2) > tileCap) continue;
-                    bool local = true;
-                    for (int q = 0; q < numQubits; q++) if ((S2 >> q & 1) && state.pos[q] >= nLocal) local = false;
-                    if (!local) continue;
-                    const size_t cnt = hyquas::runnableDense(stageGates, remaining, S2, lookahead).size();
-                    if (cnt > pickCount || (cnt == pickCount && pickSet && cnt > cur.size() && bitCount(S2) < bitCount(pickSet))) {
+                    const int cnt = countFor(S2);
+                    if (cnt > pickCount || (cnt == pickCount && pickSet && cnt > curCount && bitCount(S2) < bitCount(pickSet))) {
                         pickSet = S2; pickCount = cnt;
                     }
                 }
                 if (!pickSet) break;
                 S = pickSet;
-                cur = hyquas::runnableDense(stageGates, remaining, S, lookahead);
+                curCount = pickCount;
             }
-            if (cur.empty()) continue;
+            if (curCount <= 0) continue;
             const int m = std::max(3, bitCount(S));
-            const double rate = cur.size() / ev->denseMs30[m];
-            if (rate > bestRate * 1.0001) { bestRate = rate; bestSet = S; bestTake = cur; bestM = m; }
+            const double rate = curCount / ev->denseMs30[m];
+            if (rate > bestRate * 1.0001) { bestRate = rate; bestSet = S; bestM = m; }
         }
+        if (bestSet) bestTake = hyquas::runnableDense(stageGates, remaining, bestSet, lookahead);
         if (bestTake.empty()) break;
         const double blockMs = ev->denseMs30[bestM];
         // further blocks must pay for themselves: stop once the launch is compute-bound and the new block is slower per

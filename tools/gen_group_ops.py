@@ -203,10 +203,17 @@ def main():
                 print("}")
                 cases.append(code)
     print()
+    # dense body index: a contiguous 0..N-1 switch compiles to ONE indexed branch (the sparse switch on `code` became a
+    # tree of compares + small BRX tables, ~8 dependent branches per gate).  The planner stores the index in flags[15:8].
+    print(f"#define HQ_OP_BODIES {len(cases)}")
+    table = [255] * (max(cases) + 1)
+    for i, c in enumerate(cases):
+        table[c] = i
+    print("static const unsigned char HQ_OP_BODY_INDEX[] = {" + ", ".join(str(v) for v in table) + "};")
     print("__device__ __forceinline__ void hq_apply_op(const hq::DevOp& o) {")
-    print("    switch (o.code) {")
-    for c in cases:
-        print(f"        case {c}: hq_op_{c}(o); break;")
+    print("    switch ((o.flags >> 8) & 0xffu) {")
+    for i, c in enumerate(cases):
+        print(f"        case {i}: hq_op_{c}(o); break;")
     print("        default: break;")
     print("    }")
     print("}")

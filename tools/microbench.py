@@ -53,6 +53,11 @@ def main():
     for kind, key in ((0, "fp64_fma_tflops"), (1, "fp64_mma_tflops")):
         check(lib.hq_microbench_fp64(kind, v))
         res[key] = v.value
+    res["dmma_tflops_by_warps_per_sm"] = {}
+    for w in (4, 8, 12, 16, 24, 32):
+        check(lib.hq_microbench_fp64(10 + w, v))
+        res["dmma_tflops_by_warps_per_sm"][w] = v.value
+    print("dmma by warps/SM:", {k: round(x, 1) for k, x in res["dmma_tflops_by_warps_per_sm"].items()}, flush=True)
     st = ctypes.c_void_p()
     check(lib.hq_state_alloc(n, ctypes.byref(st)))
     check(lib.hq_microbench_copy(st, n, v))
@@ -79,6 +84,7 @@ def main():
         "h_x16_4q": (["H"], 16, hi4),
         "h_x256_4q": (["H"], 256, hi4),
     }
+    os.environ["HQ_BACKEND"] = "group"      # these cases price the TILE kernel; the hybrid partitioner would fuse them
     for name, (spec, count, qubits) in cases.items():
         c = build(n, spec, count, qubits)
         c.compile()
@@ -92,6 +98,7 @@ def main():
         print(f"{name:16s} gates={count:4d} groups={len(per)} total={min(ms, ms2):8.3f} ms  per-group={['%.2f' % x for x in per]}",
               flush=True)
         c.close()
+    os.environ.pop("HQ_BACKEND", None)
     # fused dense kernel: one or several random unitaries on m qubits, 2^n amplitudes
     import numpy as np
     rng = np.random.default_rng(5)

@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Runs a list of benchmark circuits through the public API on 1..N GPUs (one process per GPU under torch.distributed.run)
+and prints one JSON line per circuit: time ("Time Cost" semantics: execution phase only), sweeps, effective HBM TB/s,
+swap statistics, and a full-size correctness verdict that needs no oracle:
+
+  * norm            sum |a|^2 over all ranks == 1 (1e-10)
+  * known answer    qft -> uniform 2^-n/2; bv -> two amplitudes +-1/sqrt2 at known indices; hidden_shift -> |s>;
+                    adder -> the basis state computed by classical evaluation of its X/CX/CCX gates
+  * dump hash       sha256 of the printState text, to compare runs of the same circuit at different GPU counts
+
+    python -m torch.distributed.run --nproc-per-node 8 tools/run_suite.py qaoa_34 bv_36 hidden_shift_36 ...
+"""
+import hashlib
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def classical_basis_state(text):
+    """Final basis state of a circuit made only of x / cx / ccx (adder family); None if other gates occur."""
+    state = 0
+    for line in text.splitlines()[3:]:
+        line = line.strip()
+        if not line:
+            continue
+        name, ops = line.split(" ")
+        q = [int(t.split("]")[0]) for t in ops.split("[")[1:]]
+        if name == "x":
+            state ^= 1 << q[0]
+        elif name == "cx":
+            if state >> q[0] & 1:
+                state ^= 1 << q[1]
+        elif name == "ccx":
+            if (state >> q[0] & 1) and (state >> q[1] & 1):
+                state ^= 1 << q[2]
+        else:
+            return None
+    return state
+
+
+def expected_dump(name, n, text):
+    """Known-answer printState text, or None."""
+    fam = name.rsplit("_", 1)[0]
+
+    def line(i, re, im=0.0):
+        z = lambda x: 0.0 if abs(x) < 1e-14 else x
+        return "%d %.12f: %.12f %.12f\n" % (i, re * re + im * im, z(re), z(im))
+
+    head = lambda amp0: "".join(line(i, amp0 if i == 0 else 0.0) for i in range(128))
+    if fam == "qft":
+        a = 2.0 ** (-n / 2)
+        return "".join(line(i, a) for i in range(128))
+    if fam == "bv":
+        s = 1 / math.sqrt(2)
+        items = {(1 << (n - 1)) - 1: s, (1 << n) - 1: -s}
+    elif fam == "hidden_shift":
+        from hyquas_b200 import circuits as C
+        import random
+        shift = C.HIDDEN_SHIFT_28 if n == 28 else random.Random(n * 10000 + 2021).getrandbits(n)
+        items = {shift: 1.0}
+    elif fam == "adder":
+        st = classical_basis_state(text)
+        if st is None:
+            return None
+        items = {st: 1.0}
+    else:
+        return None
+    out = "".join(line(i, items.get(i, 0.0)) for i in range(128))
+    for idx in sorted(items):
+        if idx >= 128:
+            out += line(idx, items[idx])
+    return out
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from hyquas_b200 import api, circuits as C
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    if world > 1:
+        dist.init_process_group("gloo")
+    api.init()
+    reps = int(os.environ.get("HQ_SUITE_REPS", "2"))
+    for name in sys.argv[1:]:
+        text = C.generate(name)
+        t0 = time.perf_counter()
+        c = api.Circuit.from_qasm(text)
+        c.compile()
+        t_compile = time.perf_counter() - t0
+        n = c.num_qubits
+        L = n - int(math.log2(world))
+        info = c.schedule_info()
+        groups = c.groups()
+        c.prepare_state()
+        c.execute()                      # warm-up (also the run whose result is checked: the state is re-initialised below)
+        best = None
+        for _ in range(reps):
+            c.prepare_state()
+            if world > 1:
+                dist.barrier()
+            us, ms = c.execute()
+            t = torch.tensor([ms], dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        norm = torch.tensor([c.norm2()], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(norm)
+        # dump of the state after the LAST timed execution
+        c.run(copy_back=False, destroy=True)
+        dump = c.dump()
+        if rank == 0:
+            S = info["groups"]
+            bytes_ = S * 32.0 * (1 << L) * world
+            want = expected_dump(name, n, text)
+            verdict = {"norm_err": abs(float(norm.item()) - 1.0)}
+            if want is not None:
+                verdict["known_answer"] = "ok" if dump == want else "MISMATCH"
+            verdict["dump_sha256"] = hashlib.sha256(dump.encode()).hexdigest()[:16]
+            ok = verdict["norm_err"] <= 1e-10 and verdict.get("known_answer", "ok") == "ok"
+            print(json.dumps({"circuit": name, "n_gpus": world, "qubits": n, "local_qubits": L, "gates": info["gates"],
+                              "stages": info["stages"], "sweeps": S,
+                              "dense_groups": sum(g["backend"] == "dense" for g in groups),
+                              "overlap_groups": sum(g["launches"] > 1 for g in groups),
+                              "time_ms": round(best, 3), "compile_ms": round(t_compile * 1e3, 1),
+                              "effective_tbps": round(bytes_ / (best * 1e-3) / 1e12, 3),
+                              "sweeps_per_s": round(S / (best * 1e-3), 2),
+                              "predicted_ms": round(sum(g["predicted_ms"] for g in groups), 2),
+                              "check": verdict, "ok": ok}), flush=True)
+        c.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
