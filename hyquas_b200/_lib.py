@@ -53,6 +53,7 @@ _SIGS = {
     "hq_group_tile_bits": (_c.c_int, []),
     "hq_group_min_run_bits": (_c.c_int, []),
     "hq_group_plan_create": (_c.c_int, [_c.c_int, _c.c_uint64, _P(HqGate), _c.c_int, _P(_c.c_void_p)]),
+    "hq_group_plan_create_ex": (_c.c_int, [_c.c_int, _c.c_uint64, _c.c_uint64, _c.c_uint64, _P(HqGate), _c.c_int, _P(_c.c_void_p)]),
     "hq_group_plan_launch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int]),
     "hq_group_plan_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
     "hq_group_plan_table_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
@@ -61,6 +62,8 @@ _SIGS = {
     "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),
     "hq_microbench_copy": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
     "hq_dense_plan_create": (_c.c_int, [_c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int), _c.c_void_p, _P(_c.c_void_p)]),
+    "hq_dense_plan_create_ex": (_c.c_int, [_c.c_int, _c.c_uint64, _c.c_uint64, _c.c_int, _P(_c.c_int), _P(_c.c_int), _c.c_void_p,
+                                           _P(_c.c_void_p)]),
     "hq_dense_plan_launch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int]),
     "hq_dense_plan_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_double), _P(_c.c_int)]),
     "hq_dense_plan_destroy": (_c.c_int, [_c.c_void_p]),
@@ -71,6 +74,9 @@ _SIGS = {
     "hq_comm_destroy": (_c.c_int, []),
     "hq_comm_bcast_host": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int]),
     "hq_comm_allgather_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t]),
+    "hq_swap_any_position": (_c.c_int, [_P(_c.c_int)]),
+    "hq_swap_attach": (_c.c_int, [_c.c_void_p]),
+    "hq_swap_detach": (_c.c_int, []),
     "hq_state_bitswap": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int)]),
     "hq_swap_plan_create": (_c.c_int, [_c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_void_p)]),
     "hq_swap_begin": (_c.c_int, [_c.c_void_p, _c.c_void_p]),

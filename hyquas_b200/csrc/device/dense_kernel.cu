@@ -40,6 +40,7 @@ struct DenseMatDesc {
 struct DenseParams {
     double2* state;
     uint64_t ntiles;
+    uint64_t fixed_base;        // value of the fixed (non-varying) physical bits of this launch
     const double2* u_frag;      // all matrices, fragment order
     const uint16_t* tables;     // all matrices: swk | swn
     uint64_t g_high[16];        // physical offset contributed by bits 8..11 of the tile index
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, MAXM <= 4 ? 3 : 2) dense_kernel
     __syncthreads();
 
     for (uint64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
-        uint64_t base = 0;
+        uint64_t base = P.fixed_base;
         for (int s = 0; s < P.nseg; ++s) base |= ((t >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
         double2* gbase = P.state + base + g_low;
         for (int i = 0; i < per_thread; ++i) cp_async16(tile_s + ((s_low ^ P.f_high[i]) << 4), gbase + P.g_high[i]);
@@ -207,9 +208,15 @@ struct hq_dense_plan {
 // (U[row + col * 2^m], like the A operand of the reference's cublasZgemm call), interleaved re/im.
 extern "C" int hq_dense_plan_create(int L, int nmat, const int* m_list, const int* qubit_pos, const double* u_colmajor,
                                     hq_dense_plan** out) {
+    return hq_dense_plan_create_ex(L, 0, 0, nmat, m_list, qubit_pos, u_colmajor, out);
+}
+
+extern "C" int hq_dense_plan_create_ex(int L, uint64_t fixed_mask, uint64_t fixed_value, int nmat, const int* m_list,
+                                       const int* qubit_pos, const double* u_colmajor, hq_dense_plan** out) {
+    HQ_REQUIRE((fixed_mask >> L) == 0 && (fixed_value & ~fixed_mask) == 0, "fixed bits must be local and fixed_value within fixed_mask");
     HQ_REQUIRE(out && nmat >= 1 && nmat <= DENSE_MAX_MATS && m_list && qubit_pos && u_colmajor, "bad arguments to hq_dense_plan_create");
-    HQ_REQUIRE(L >= 8 && L <= 40, "local qubit count out of range for the dense kernel");
-    const int Kt = std::min(12, L);
+    HQ_REQUIRE(L - popcount64(fixed_mask) >= 8 && L <= 40, "local qubit count out of range for the dense kernel");
+    const int Kt = std::min(12, L - popcount64(fixed_mask));
     // ---- tile = union of all matrix bits + lowest free physical bits ----
     uint64_t tile_mask = 0;
     {
@@ -219,6 +226,7 @@ extern "C" int hq_dense_plan_create(int L, int nmat, const int* m_list, const in
             uint64_t seen = 0;
             for (int b = 0; b < m_list[i]; ++b, ++qp) {
                 HQ_REQUIRE(*qp >= 0 && *qp < L, "matrix qubit outside the local state");
+                HQ_REQUIRE(!(fixed_mask >> *qp & 1), "matrix qubit on a fixed bit");
                 HQ_REQUIRE(!(seen >> *qp & 1), "matrix qubits must be distinct");
                 seen |= 1ull << *qp;
             }
@@ -227,7 +235,8 @@ extern "C" int hq_dense_plan_create(int L, int nmat, const int* m_list, const in
     }
     HQ_REQUIRE(popcount64(tile_mask) <= Kt - 3 || popcount64(tile_mask | 7ull) <= Kt, "matrices span too many qubits for one tile");
     tile_mask |= 7ull;   // >= 128-byte runs
-    for (int b = 0; b < L && popcount64(tile_mask) < Kt; ++b) tile_mask |= 1ull << b;
+    HQ_REQUIRE((fixed_mask & 7ull) == 0, "physical bits 0..2 cannot be fixed");
+    for (int b = 0; b < L && popcount64(tile_mask) < Kt; ++b) if (!(fixed_mask >> b & 1)) tile_mask |= 1ull << b;
     HQ_REQUIRE(popcount64(tile_mask) == Kt, "matrices span too many qubits for one tile");
     int phys_to_tile[64];
     for (int i = 0; i < 64; ++i) phys_to_tile[i] = -1;
@@ -366,7 +375,8 @@ extern "C" int hq_dense_plan_create(int L, int nmat, const int* m_list, const in
     }
     plan->L = L; plan->Kt = Kt; plan->nmat = nmat;
     p.Kt = Kt; p.nmat = nmat;
-    p.ntiles = 1ull << (L - Kt);
+    p.ntiles = 1ull << (L - Kt - popcount64(fixed_mask));
+    p.fixed_base = fixed_value;
     p.u_total = (uint32_t)ufrag.size();
     p.tab_total = (uint32_t)tables.size();
     std::memcpy(p.fvec, fvec, 12);
@@ -378,7 +388,7 @@ extern "C" int hq_dense_plan_create(int L, int nmat, const int* m_list, const in
         p.f_high[i] = (uint16_t)(swz(j));
     }
     {
-        const uint64_t outmask = ((1ull << L) - 1) & ~tile_mask;
+        const uint64_t outmask = ((1ull << L) - 1) & ~tile_mask & ~fixed_mask;
         int nseg = 0, src = 0, b = 0;
         while (b < L) {
             if (!(outmask >> b & 1)) { ++b; continue; }
@@ -427,7 +437,7 @@ extern "C" int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int 
     HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, DENSE_THREADS, plan->smem));
     DenseParams p = plan->p;
     p.state = static_cast<double2*>(state);
-    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)rt().sm_count * std::max(1, nb));
+    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * std::max(1, nb) - rt().reserved_ctas));
     kern<<<plan->grid, DENSE_THREADS, plan->smem, on_comm_stream ? rt().comm : rt().compute>>>(p);
     HQ_CUDA(cudaGetLastError());
     return HQ_OK;
@@ -473,7 +483,7 @@ extern "C" int hq_debug_dense_plan_emulate(const hq_dense_plan* plan, double* st
     double2* st = reinterpret_cast<double2*>(state_re_im);
     std::vector<double2> tile(TILE), y;
     for (uint64_t t = 0; t < p.ntiles; ++t) {
-        uint64_t base = 0;
+        uint64_t base = p.fixed_base;
         for (int s = 0; s < p.nseg; ++s) base |= ((t >> p.seg_src[s]) & p.seg_mask[s]) << p.seg_shift[s];
         std::vector<uint64_t> goff(TILE);
         std::vector<uint32_t> spos(TILE);

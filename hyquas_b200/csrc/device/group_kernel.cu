@@ -110,7 +110,7 @@ __device__ __forceinline__ void op_diag_run(const DevOp* entries, int n, uint64_
 template <int K>
 __device__ __forceinline__ void issue_tile_load(const GroupParams& P, uint64_t t, double2* tile, uint64_t* bar,
                                                 uint64_t* tbase_s, int lane) {
-    uint64_t base = 0;
+    uint64_t base = P.fixed_base;
     for (int s = 0; s < P.nseg; ++s) base |= ((t >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
     if (lane == 0) {
         *tbase_s = base;
@@ -264,10 +264,19 @@ extern "C" int hq_group_tile_bits(void) { return rt().tile_bits; }
 extern "C" int hq_group_min_run_bits(void) { return MIN_RUN_BITS; }
 
 extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* gates, int ngates, hq_group_plan** out) {
+    return hq_group_plan_create_ex(L, tile_mask, 0, 0, gates, ngates, out);
+}
+
+// fixed_mask / fixed_value: physical local bits that do NOT vary in this launch (the launch covers only the amplitudes
+// whose fixed bits equal fixed_value): one chunk of a state whose other chunks are still being exchanged.
+extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed_mask, uint64_t fixed_value, const hq_gate* gates,
+                                       int ngates, hq_group_plan** out) {
     HQ_REQUIRE(out != nullptr, "plan out pointer is null");
+    HQ_REQUIRE((fixed_mask >> L) == 0 && (fixed_mask & tile_mask) == 0 && (fixed_value & ~fixed_mask) == 0,
+               "fixed bits must be local, outside the tile, and fixed_value within fixed_mask");
     const int K = popcount64(tile_mask);
     HQ_REQUIRE(K >= 10 && K <= 12, "tile_mask must select 10, 11 or 12 bits");
-    HQ_REQUIRE(L >= K && L <= 40, "local qubit count out of range for the gate-group kernel");
+    HQ_REQUIRE(L - popcount64(fixed_mask) >= K && L <= 40, "local qubit count out of range for the gate-group kernel");
     HQ_REQUIRE((tile_mask >> L) == 0, "tile_mask has bits outside the local state");
     HQ_REQUIRE((tile_mask & ((1ull << MIN_RUN_BITS) - 1)) == ((1ull << MIN_RUN_BITS) - 1),
                "tile_mask must contain the low hq_group_min_run_bits() bits");
@@ -286,6 +295,8 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
         const hq_gate& g = gates[i];
         HQ_REQUIRE(g.target >= -1 && g.target < L, "gate target outside the local state");
         HQ_REQUIRE(g.control >= -1 && g.control < L && g.control2 >= -1 && g.control2 < L, "gate control outside the local state");
+        for (int q : {g.target, g.control, g.control2})
+            HQ_REQUIRE(q < 0 || !(fixed_mask >> q & 1), "gate touches a fixed bit (resolve it when lowering the gate)");
         HostGate h{};
         h.target_phys = g.target; h.c1_phys = g.control; h.c2_phys = g.control2;
         if (!classify(g, h)) continue;
@@ -481,13 +492,14 @@ extern "C" int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* ga
     plan->L = L; plan->K = K; plan->NT = NT; plan->tile_mask = tile_mask;
     plan->nrounds = nrounds; plan->nops = (int)dops.size(); plan->ngates = (int)hg.size();
     GroupParams& p = plan->p;
-    p.ntiles = 1ull << (L - K);
+    p.ntiles = 1ull << (L - K - popcount64(fixed_mask));
+    p.fixed_base = fixed_value;
     p.nruns = nruns;
     p.run_bytes = 16u << run_bits;
     p.nrounds = nrounds;
     p.nops = (int)dops.size();
     {   // tile number -> base: scatter over the runs of bits NOT in the tile
-        const uint64_t outmask = ((1ull << L) - 1) & ~tile_mask;
+        const uint64_t outmask = ((1ull << L) - 1) & ~tile_mask & ~fixed_mask;
         int nseg = 0, src = 0, b = 0;
         while (b < L) {
             if (!(outmask >> b & 1)) { ++b; continue; }
@@ -552,7 +564,8 @@ static int launch_k(const hq_group_plan* plan, GroupParams p, cudaStream_t s) {
         HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, plan->NT, plan->smem));
         it = occupancy.emplace(plan->smem, std::max(1, nb)).first;
     }
-    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)rt().sm_count * it->second);
+    // a swap kernel in flight holds one CTA slot on `reserved_ctas` SMs: leave those slots free (no second wave)
+    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * it->second - rt().reserved_ctas));
     kern<<<plan->grid, plan->NT, plan->smem, s>>>(p);
     HQ_CUDA(cudaGetLastError());
     return HQ_OK;

@@ -58,6 +58,7 @@ struct alignas(16) DevRound {
 struct GroupParams {
     double2* state;
     uint64_t ntiles;
+    uint64_t fixed_base;       // value of the fixed (non-varying) physical bits of this launch
     const uint64_t* run_off;   // [nruns] physical offset of each contiguous run inside a tile
     const DevRound* rounds;
     const DevOp* ops;

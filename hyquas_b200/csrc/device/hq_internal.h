@@ -36,6 +36,7 @@ struct Runtime {
     cudaStream_t comm = nullptr;      // global<->local qubit swaps
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int tile_bits = 12;               // K of the gate-group kernel
+    int reserved_ctas = 0;            // CTAs of a swap kernel in flight on the comm stream (one per SM)
     bool relaxed_regs = false;        // trade resident CTAs for registers in the gate-group kernel
 };
 Runtime& rt();

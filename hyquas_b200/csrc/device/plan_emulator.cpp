@@ -108,7 +108,7 @@ extern "C" int hq_debug_group_plan_emulate(const hq_group_plan* plan, double* st
     const uint32_t run_amps = P.run_bytes >> 4;
     std::vector<Amp> sm(TILE), regs((size_t)NT * R);
     for (uint64_t t = 0; t < P.ntiles; ++t) {
-        uint64_t base = 0;
+        uint64_t base = P.fixed_base;
         for (int s = 0; s < P.nseg; ++s) base |= ((t >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
         for (int q = 0; q < P.nruns; ++q)   // the producer warp's bulk copies
             std::memcpy(&sm[(size_t)q * run_amps], &state[base + run_off[q]], P.run_bytes);

@@ -13,6 +13,13 @@
 //     extra memory is 2 pieces instead of a second state vector;
 //   * one CUDA event per chunk: the compute stream waits for exactly the chunk it is about to run the overlap
 //     groups on, while later chunks are still on the wire.
+// Two transports for the data, selected at hq_comm_init (HQ_SWAP=p2p|nccl, default p2p when every GPU pair is peer-capable):
+//   p2p   the state allocations are mapped into every process with CUDA IPC; ONE kernel per step swaps the two chunks of a
+//         pair element by element over NVLink (each GPU handles half of the pair: remote load + remote store), truly in
+//         place: no staging, no un-stage copy, and the swapped local bits may sit ANYWHERE (>= bit 3), so no local
+//         bit-permutation sweep is needed either.  NCCL only carries the barriers (a tiny all-reduce before, a 1-element
+//         send/recv pair after each step).
+//   nccl  the staging-ring path described above (needs the swapped bits at the top of the local index).
 // NCCL is bound with dlopen (libnccl.so.2) so that single-GPU use never needs it.
 #include <dlfcn.h>
 #include <nccl.h>
@@ -47,6 +54,11 @@ struct Comm {
     double2* staging = nullptr;         // 2 slots of piece_amps
     uint64_t piece_amps = 0;
     cudaEvent_t slot_filled[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
+    bool p2p = false;                   // transport (decided at init)
+    std::vector<double2*> peer_state;   // p2p: every rank's state allocation mapped here (own entry = own pointer)
+    void* attached = nullptr;
+    double* sync_buf = nullptr;         // 2 doubles for the barrier collectives
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 };
 static Comm& cm() {
     static Comm c;
@@ -93,6 +105,7 @@ static int load_nccl() {
     a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
     a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    cm().AllReduce = reinterpret_cast<decltype(cm().AllReduce)>(sym("ncclAllReduce"));
     if (!ok) {
         set_error("libnccl lacks a required symbol");
         return HQ_ERR_NCCL;
@@ -123,6 +136,49 @@ __global__ void bitswap_kernel(double2* s, uint64_t n, const BitSwaps bs) {
     }
 }
 
+// p2p transport: swap mine[scatter(z) | mine_bits] with peer[scatter(z) | peer_bits] for z in [z0, z0 + count).
+// scatter() spreads the bits of z over the local index positions that are NOT being swapped.
+struct XchgParams {
+    double2* mine;
+    double2* peer;
+    uint64_t mine_bits, peer_bits, z0, count;
+    int nseg;
+    uint8_t seg_shift[8], seg_src[8];
+    uint64_t seg_mask[8];
+};
+// Few CTAs (they must leave room for the gate groups that run under the exchange), so every thread keeps XCHG_UNROLL
+// remote loads in flight to cover the NVLink round trip.
+constexpr int XCHG_UNROLL = 8;
+__global__ void __launch_bounds__(512) xchg_kernel(const __grid_constant__ XchgParams P) {
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t i0 = tid; i0 < P.count; i0 += nthreads * XCHG_UNROLL) {
+        double2 *pm[XCHG_UNROLL], *pp[XCHG_UNROLL];
+        double2 a[XCHG_UNROLL], b[XCHG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < XCHG_UNROLL; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * nthreads;   // consecutive threads stay on consecutive amplitudes
+            const uint64_t z = P.z0 + (i < P.count ? i : i0);
+            uint64_t idx = 0;
+#pragma unroll 1
+            for (int s = 0; s < P.nseg; ++s) idx |= ((z >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
+            pm[u] = P.mine + (idx | P.mine_bits);
+            pp[u] = P.peer + (idx | P.peer_bits);
+        }
+#pragma unroll
+        for (int u = 0; u < XCHG_UNROLL; ++u) b[u] = *pp[u];
+#pragma unroll
+        for (int u = 0; u < XCHG_UNROLL; ++u) a[u] = *pm[u];
+#pragma unroll
+        for (int u = 0; u < XCHG_UNROLL; ++u) {
+            if (i0 + (uint64_t)u * nthreads < P.count) {
+                *pm[u] = b[u];
+                *pp[u] = a[u];
+            }
+        }
+    }
+}
+
 __global__ void unstage_kernel(const double2* __restrict__ src, double2* __restrict__ dst, uint64_t n) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
@@ -139,6 +195,14 @@ struct hq_swap_plan {
     std::vector<cudaEvent_t> landed;  // landed[c]: chunk c holds its post-swap contents
     cudaEvent_t compute_done = nullptr, all_done = nullptr;
     int next = 0;
+    bool top = false;                 // swapped local bits are the top k positions (contiguous chunks)
+    std::vector<int> local_bits;
+    hq::XchgParams xp{};              // p2p: segment tables (z -> index with holes at the swapped positions)
+    uint64_t chunk_bits(int c) const {
+        uint64_t v = 0;
+        for (int i = 0; i < k; ++i) if (c >> i & 1) v |= 1ull << local_bits[i];
+        return v;
+    }
 };
 
 extern "C" int hq_comm_unique_id(unsigned char out[128]) {
@@ -164,6 +228,28 @@ extern "C" int hq_comm_init(int world, int rank, const unsigned char id_bytes[12
     HQ_NCCL(c.api.CommInitRank(&c.comm, world, id, rank));
     c.world = world;
     c.rank = rank;
+    HQ_CUDA(cudaMalloc(&c.sync_buf, 4 * sizeof(double)));
+    HQ_CUDA(cudaMemset(c.sync_buf, 0, 4 * sizeof(double)));
+    {   // transport: p2p needs every visible GPU pair to be peer-capable (NVSwitch boxes are)
+        const char* e = getenv("HQ_SWAP");
+        bool want = !e || std::string(e) != "nccl";
+        int ndev = 0;
+        HQ_CUDA(cudaGetDeviceCount(&ndev));
+        for (int d = 0; d < ndev && want; ++d) {
+            if (d == rt().device) continue;
+            int can = 0;
+            HQ_CUDA(cudaDeviceCanAccessPeer(&can, rt().device, d));
+            if (!can) want = false;
+        }
+        if (ndev < world) want = false;   // ranks on other nodes / hidden devices: IPC mapping impossible
+        // every rank must take the same decision
+        double flag = want ? 1.0 : 0.0, *d = c.sync_buf;
+        HQ_CUDA(cudaMemcpy(d, &flag, sizeof(double), cudaMemcpyHostToDevice));
+        HQ_NCCL(c.AllReduce(d, d + 1, 1, ncclDouble, ncclMin, c.comm, rt().comm));
+        HQ_CUDA(cudaStreamSynchronize(rt().comm));
+        HQ_CUDA(cudaMemcpy(&flag, d + 1, sizeof(double), cudaMemcpyDeviceToHost));
+        c.p2p = flag > 0.5;
+    }
     HQ_CUDA(cudaStreamCreateWithFlags(&c.unstage, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         HQ_CUDA(cudaEventCreateWithFlags(&c.slot_filled[i], cudaEventDisableTiming));
@@ -178,6 +264,55 @@ extern "C" int hq_comm_info(int* world, int* rank) {
     return HQ_OK;
 }
 
+extern "C" int hq_swap_detach(void);
+
+// 1 when swaps may name ANY local bit >= 3 (p2p transport), 0 when they must be the top k local bits (nccl transport).
+extern "C" int hq_swap_any_position(int* any) {
+    HQ_REQUIRE(any != nullptr, "null out pointer");
+    *any = cm().p2p ? 1 : 0;
+    return HQ_OK;
+}
+
+// p2p transport: map every rank's state allocation into this process (collective; call after the state is allocated,
+// outside the timed region).  No-op for the nccl transport.
+extern "C" int hq_swap_attach(void* state) {
+    Comm& c = cm();
+    HQ_REQUIRE(c.comm && state, "communicator not initialised");
+    if (!c.p2p || c.attached == state) return HQ_OK;
+    if (c.attached) hq_swap_detach();
+    cudaIpcMemHandle_t mine;
+    HQ_CUDA(cudaIpcGetMemHandle(&mine, state));
+    std::vector<cudaIpcMemHandle_t> all(c.world);
+    int rc = hq_comm_allgather_host(&mine, all.data(), sizeof(mine));
+    if (rc != HQ_OK) return rc;
+    c.peer_state.assign(c.world, nullptr);
+    for (int r = 0; r < c.world; ++r) {
+        if (r == c.rank) { c.peer_state[r] = static_cast<double2*>(state); continue; }
+        void* p = nullptr;
+        HQ_CUDA(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        c.peer_state[r] = static_cast<double2*>(p);
+    }
+    c.attached = state;
+    return HQ_OK;
+}
+
+extern "C" int hq_swap_detach(void) {
+    Comm& c = cm();
+    if (!c.attached) return HQ_OK;
+    cudaStreamSynchronize(rt().comm);
+    cudaStreamSynchronize(rt().compute);
+    // nobody may unmap (or free) while a peer still has exchanges in flight on this memory
+    if (c.comm) {
+        c.AllReduce(c.sync_buf, c.sync_buf + 1, 1, ncclDouble, ncclSum, c.comm, rt().comm);
+        cudaStreamSynchronize(rt().comm);
+    }
+    for (int r = 0; r < c.world; ++r)
+        if (r != c.rank && c.peer_state[r]) cudaIpcCloseMemHandle(c.peer_state[r]);
+    c.peer_state.clear();
+    c.attached = nullptr;
+    return HQ_OK;
+}
+
 extern "C" int hq_comm_destroy(void) {
     Comm& c = cm();
     if (!c.comm) return HQ_OK;
@@ -185,8 +320,11 @@ extern "C" int hq_comm_destroy(void) {
     cudaStreamSynchronize(c.unstage);
     c.api.CommDestroy(c.comm);
     c.comm = nullptr;
+    hq_swap_detach();
     if (c.staging) cudaFree(c.staging);
     c.staging = nullptr;
+    if (c.sync_buf) cudaFree(c.sync_buf);
+    c.sync_buf = nullptr;
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c.slot_filled[i]);
         cudaEventDestroy(c.slot_free[i]);
@@ -247,8 +385,9 @@ extern "C" int hq_state_bitswap(void* state, int L, int npairs, const int* a, co
     return HQ_OK;
 }
 
-// local_bits must be the top k local positions (L-k .. L-1, ascending): chunks are then contiguous.
-// global_bits[i] (0-based above L) is the global bit traded with local_bits[i].
+// local_bits[i] (physical local position) trades places with global bit global_bits[i] (0-based above L).
+// nccl transport: local_bits must be the top k local positions, ascending (contiguous chunks).
+// p2p transport: any distinct positions >= 3.
 extern "C" int hq_swap_plan_create(int L, int k, const int* local_bits, const int* global_bits, hq_swap_plan** out) {
     Comm& c = cm();
     HQ_REQUIRE(out && k >= 1 && k <= 6 && L > k, "bad arguments to hq_swap_plan_create");
@@ -259,13 +398,24 @@ extern "C" int hq_swap_plan_create(int L, int k, const int* local_bits, const in
     auto* p = new hq_swap_plan();
     p->L = L;
     p->k = k;
+    p->top = true;
+    uint64_t lmask = 0;
     for (int i = 0; i < k; ++i) {
-        if (local_bits[i] != L - k + i || global_bits[i] < 0 || global_bits[i] >= g) {
+        const bool bad = local_bits[i] < 3 || local_bits[i] >= L || (lmask >> local_bits[i] & 1) || global_bits[i] < 0 || global_bits[i] >= g;
+        if (bad) {
             delete p;
-            set_error("swap plan: local bits must be the top k local positions and global bits must exist");
+            set_error("swap plan: local bits must be distinct positions in [3, L) and global bits must exist");
             return HQ_ERR_ARG;
         }
+        if (local_bits[i] != L - k + i) p->top = false;
+        lmask |= 1ull << local_bits[i];
+        p->local_bits.push_back(local_bits[i]);
         p->myc |= ((c.rank >> global_bits[i]) & 1) << i;
+    }
+    if (!p->top && !c.p2p) {
+        delete p;
+        set_error("swap plan: the nccl transport needs the swapped bits at the top k local positions");
+        return HQ_ERR_ARG;
     }
     p->peer.assign(1 << k, c.rank);
     for (int xr = 1; xr < (1 << k); ++xr) {
@@ -273,6 +423,18 @@ extern "C" int hq_swap_plan_create(int L, int k, const int* local_bits, const in
         int r = c.rank;
         for (int i = 0; i < k; ++i) r = (r & ~(1 << global_bits[i])) | (((ch >> i) & 1) << global_bits[i]);
         p->peer[xr] = r;
+    }
+    {   // z (L-k bits) -> local index with zeros at the swapped positions
+        const uint64_t keep = ((1ull << L) - 1) & ~lmask;
+        int nseg = 0, src = 0, b = 0;
+        while (b < L) {
+            if (!(keep >> b & 1)) { ++b; continue; }
+            int e = b;
+            while (e < L && (keep >> e & 1)) ++e;
+            p->xp.seg_shift[nseg] = (uint8_t)b; p->xp.seg_src[nseg] = (uint8_t)src; p->xp.seg_mask[nseg] = (1ull << (e - b)) - 1;
+            src += e - b; ++nseg; b = e;
+        }
+        p->xp.nseg = nseg;
     }
     p->landed.resize(1 << k);
     for (auto& e : p->landed) HQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -297,6 +459,40 @@ extern "C" int hq_swap_begin(hq_swap_plan* p, void* state_v) {
     HQ_REQUIRE(p && state_v && c.comm, "bad arguments to hq_swap_begin");
     double2* state = static_cast<double2*>(state_v);
     const uint64_t chunk_amps = 1ull << (p->L - p->k);
+    if (c.p2p) {
+        HQ_REQUIRE(c.attached == state_v, "hq_swap_attach(state) must be called before a p2p swap");
+        cudaStream_t comm = rt().comm;
+        HQ_CUDA(cudaEventRecord(p->compute_done, rt().compute));
+        HQ_CUDA(cudaStreamWaitEvent(comm, p->compute_done, 0));
+        HQ_CUDA(cudaEventRecord(p->landed[p->myc], comm));   // nobody else touches the chunk that stays
+        // every rank's earlier compute must be finished before anybody reads or writes its memory
+        HQ_NCCL(c.AllReduce(c.sync_buf, c.sync_buf + 1, 1, ncclDouble, ncclSum, c.comm, comm));
+        int ctas = 32;
+        if (const char* e = getenv("HQ_SWAP_CTAS")) ctas = std::max(1, atoi(e));
+        rt().reserved_ctas = ctas;   // gate-group launches under the exchange size their grids around these CTAs
+        for (int xr = 1; xr < (1 << p->k); ++xr) {
+            const int ch = p->myc ^ xr, peer = p->peer[xr];
+            XchgParams xp = p->xp;
+            xp.mine = state;
+            xp.peer = c.peer_state[peer];
+            xp.mine_bits = p->chunk_bits(ch);
+            xp.peer_bits = p->chunk_bits(p->myc);
+            xp.count = chunk_amps / 2;
+            xp.z0 = c.rank < peer ? 0 : chunk_amps / 2;
+            xchg_kernel<<<ctas, 512, 0, comm>>>(xp);
+            HQ_CUDA(cudaGetLastError());
+            // pairwise barrier: the chunk is complete once BOTH halves are done
+            HQ_NCCL(c.api.GroupStart());
+            HQ_NCCL(c.api.Send(c.sync_buf + 2, 1, ncclDouble, peer, c.comm, comm));
+            HQ_NCCL(c.api.Recv(c.sync_buf + 3, 1, ncclDouble, peer, c.comm, comm));
+            HQ_NCCL(c.api.GroupEnd());
+            HQ_CUDA(cudaEventRecord(p->landed[ch], comm));
+        }
+        HQ_CUDA(cudaEventRecord(p->all_done, comm));
+        p->next = 0;
+        return HQ_OK;
+    }
+    HQ_REQUIRE(p->top, "the nccl transport needs the swapped bits at the top k local positions");
     uint64_t piece = 1ull << 22;   // 64 MiB of amplitudes
     if (const char* e = getenv("HQ_SWAP_PIECE_LOG2")) piece = 1ull << std::max(10, std::min(atoi(e), 30));
     piece = std::min(piece, chunk_amps);
@@ -352,6 +548,7 @@ extern "C" int hq_swap_wait_chunk(hq_swap_plan* p, int* chunk) {
 // After this the compute stream is ordered behind the whole exchange (and the next swap behind compute).
 extern "C" int hq_swap_end(hq_swap_plan* p) {
     HQ_REQUIRE(p != nullptr, "null swap plan");
+    rt().reserved_ctas = 0;
     HQ_CUDA(cudaStreamWaitEvent(rt().compute, p->all_done, 0));
     return HQ_OK;
 }

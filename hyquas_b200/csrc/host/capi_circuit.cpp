@@ -260,11 +260,9 @@ extern "C" int hq_debug_stage_swap(hq_circuit* h, int stage, int* npairs, int* p
 extern "C" int hq_debug_stage_emulate(hq_circuit* h, int stage, int phase, int chunk, double* state_re_im) {
     if (!h || !state_re_im || stage < 0 || stage >= (int)h->c->getSchedule().localGroups.size()) { g_cerr = "bad stage"; return HQ_ERR_ARG; }
     const LocalGroup& lg = h->c->getSchedule().localGroups[stage];
-    const int L = h->c->numQubits - MyGlobalVars::bit, k = (int)lg.swap.localBit.size();
     if (phase == 0) {
-        double* base = state_re_im + 2 * ((size_t)chunk << (L - k));
-        for (const auto& gg : lg.overlapGroups) {
-            int rc = emulateGroup(gg, chunk, base);
+        for (const auto& gg : lg.overlapGroups) {   // a per-chunk plan carries its chunk's fixed bits: whole shard pointer
+            int rc = emulateGroup(gg, chunk, state_re_im);
             if (rc != HQ_OK) return rc;
         }
     } else {

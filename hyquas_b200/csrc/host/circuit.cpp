@@ -22,6 +22,7 @@ Circuit::~Circuit() {
 }
 
 void Circuit::destroyState() {
+    if (!deviceStateVec.empty() && MyGlobalVars::numGPUs > 1 && !MyGlobalVars::hostOnly) checkHq(hq_swap_detach());
     for (auto* p : deviceStateVec) hq_state_free(p);
     deviceStateVec.clear();
 }
@@ -56,6 +57,7 @@ void Circuit::prepareState() {
         void* st = nullptr;
         checkHq(hq_state_alloc(L, &st));
         deviceStateVec.assign(1, static_cast<qComplex*>(st));
+        if (MyGlobalVars::numGPUs > 1) checkHq(hq_swap_attach(st));   // p2p transport: map the peers' shards (collective)
     }
     checkHq(hq_state_init(deviceStateVec[0], L, MyMPI::rank == 0));
     checkHq(hq_sync());

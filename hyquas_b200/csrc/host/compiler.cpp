@@ -55,31 +55,51 @@ std::vector<int> runnableDense(const std::vector<Gate>& gates, const std::vector
     return out;
 }
 
-// Move to a layout in which exactly `newLocals` are local.  Outgoing qubits are first brought to the top
-// local positions (in-place bit swaps), then traded with the global positions of the incoming qubits.
-SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal) {
+// Move to a layout in which exactly `newLocals` are local: every outgoing qubit trades places with one incoming qubit.
+// With the p2p transport (anyBit) the outgoing qubit is traded from wherever it sits (positions < 3 excepted: they stay
+// in every tile); with the nccl transport outgoing qubits are first brought to the top local positions by in-place bit
+// swaps so that the chunks are contiguous.
+SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal, bool anyBit) {
     SwapPlan plan;
     std::vector<int> outgoing, incoming;
     for (int p = 0; p < numLocal; p++) if (!(newLocals >> state.layout[p] & 1)) outgoing.push_back(state.layout[p]);
     for (int p = numLocal; p < numQubits; p++) if (newLocals >> state.layout[p] & 1) incoming.push_back(state.layout[p]);
     assert(outgoing.size() == incoming.size());
     const int k = (int)outgoing.size();
-    // outgoing qubits that already sit in the top-k window keep their place
-    std::vector<int> slots;
-    for (int p = numLocal - k; p < numLocal; p++) slots.push_back(p);
-    std::vector<int> movers;
-    for (int q : outgoing) {
-        auto it = std::find(slots.begin(), slots.end(), state.pos[q]);
-        if (it != slots.end()) slots.erase(it); else movers.push_back(q);
-    }
-    for (size_t i = 0; i < movers.size(); i++) {
-        const int a = state.pos[movers[i]], b = slots[i];
-        plan.localPerm.push_back({a, b});
-        state.swapPhysical(a, b);
+    if (anyBit) {
+        const int minBit = 5;   // positions below stay in every tile (pinnedBits) and are never traded
+        for (int q : outgoing) {
+            if (state.pos[q] >= minBit) continue;
+            // rare: an outgoing qubit sits in the always-in-tile low bits; move it to the highest staying position
+            for (int p = numLocal - 1; p >= minBit; p--) {
+                const int other = state.layout[p];
+                if (std::find(outgoing.begin(), outgoing.end(), other) != outgoing.end()) continue;
+                plan.localPerm.push_back({state.pos[q], p});
+                state.swapPhysical(state.pos[q], p);
+                break;
+            }
+        }
+        std::sort(outgoing.begin(), outgoing.end(), [&](int x, int y) { return state.pos[x] < state.pos[y]; });
+    } else {
+        // outgoing qubits that already sit in the top-k window keep their place
+        std::vector<int> slots;
+        for (int p = numLocal - k; p < numLocal; p++) slots.push_back(p);
+        std::vector<int> movers;
+        for (int q : outgoing) {
+            auto it = std::find(slots.begin(), slots.end(), state.pos[q]);
+            if (it != slots.end()) slots.erase(it); else movers.push_back(q);
+        }
+        for (size_t i = 0; i < movers.size(); i++) {
+            const int a = state.pos[movers[i]], b = slots[i];
+            plan.localPerm.push_back({a, b});
+            state.swapPhysical(a, b);
+        }
+        outgoing.clear();
+        for (int p = numLocal - k; p < numLocal; p++) outgoing.push_back(state.layout[p]);
     }
     std::sort(incoming.begin(), incoming.end(), [&](int x, int y) { return state.pos[x] < state.pos[y]; });
     for (int i = 0; i < k; i++) {
-        const int lb = numLocal - k + i, gb = state.pos[incoming[i]];
+        const int lb = state.pos[outgoing[i]], gb = state.pos[incoming[i]];
         plan.localBit.push_back(lb);
         plan.globalBit.push_back(gb - numLocal);
         state.swapPhysical(lb, gb);
@@ -92,8 +112,8 @@ SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal) {
 Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
     : numQubits(numQubits_), numLocal(numQubits_ - MyGlobalVars::bit), gates(std::move(inputGates)) {
     tileBits = std::min(hq_group_tile_bits(), numLocal);
-    pinnedBits = std::min(5, tileBits);
-    if (const char* e = getenv("HQ_PINNED_BITS")) pinnedBits = std::max(hq_group_min_run_bits(), std::min(atoi(e), tileBits));
+    pinnedBits = std::min(5, tileBits);   // planSwap relies on pinnedBits <= 5
+    if (const char* e = getenv("HQ_PINNED_BITS")) pinnedBits = std::max(hq_group_min_run_bits(), std::min(atoi(e), std::min(5, tileBits)));
     backendMode = 4;   // the reference's BACKEND numbering: 1 = group (tile kernel only), 3 = blas (dense only), 4 = mix
     if (const char* e = getenv("HQ_BACKEND")) {
         const std::string v = e;
@@ -159,13 +179,14 @@ std::vector<Compiler::Stage> Compiler::splitStages() const {
 // lowest physical bits, fit one 12-bit tile.  Blocks are grown greedily from the frontier: repeatedly merge the qubits
 // of the gate that lets the block absorb the most additional gates.
 GateGroup Compiler::denseCandidate(const std::vector<Gate>& stageGates, const std::vector<int>& remaining0, const State& state,
-                                   int nLocal) const {
+                                   int nLocal, qindex exclude) const {
+    const int nEff = nLocal - bitCount(exclude);   // qubits that vary in this launch
     Evaluator* ev = Evaluator::getInstance();
     GateGroup gg;
     gg.backend = Backend::BLAS;
     gg.state = state;
     std::vector<int> remaining = remaining0;
-    const int lookahead = 512, tileCap = std::min(12, nLocal);
+    const int lookahead = 512, tileCap = std::min(12, nEff);
     qindex tileQubits = 0;   // logical qubits whose physical bits the launch's tile must contain
     for (int p = 0; p < std::min(3, nLocal); p++) tileQubits |= qindex(1) << state.layout[p];
     auto qubitsOf = [](const Gate& g) {
@@ -186,7 +207,8 @@ GateGroup Compiler::denseCandidate(const std::vector<Gate>& stageGates, const st
             int cnt = -1;
             if (bitCount(tileQubits | S2) <= tileCap) {
                 bool local = true;
-                for (int q = 0; q < numQubits; q++) if ((S2 >> q & 1) && state.pos[q] >= nLocal) local = false;
+                for (int q = 0; q < numQubits; q++)
+                    if ((S2 >> q & 1) && (state.pos[q] >= nLocal || (exclude >> state.pos[q] & 1))) local = false;
                 if (local) cnt = (int)hyquas::runnableDense(stageGates, remaining, S2, lookahead).size();
             }
             memo.emplace(S2, cnt);
@@ -247,16 +269,18 @@ GateGroup Compiler::denseCandidate(const std::vector<Gate>& stageGates, const st
     }
     std::vector<int> ms;
     for (auto& b : gg.blocks) ms.push_back(std::max(3, bitCount(b.qubits)));
-    gg.predictedMs = gg.blocks.empty() ? 0 : ev->perfDense(nLocal, ms);
+    gg.predictedMs = gg.blocks.empty() ? 0 : ev->perfDense(nEff, ms);
     return gg;
 }
 
 // ---- gate groups inside one stage ----------------------------------------------------------------------
-std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal) const {
+// `exclude`: local physical positions that do not vary in these launches (the swapped positions of a per-chunk group).
+std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal, qindex exclude) const {
+    const int nEff = nLocal - bitCount(exclude);
     std::vector<GateGroup> groups;
     std::vector<int> remaining(stageGates.size());
     for (size_t i = 0; i < stageGates.size(); i++) remaining[i] = (int)i;
-    const int K = std::min(tileBits, nLocal), C = std::min(pinnedBits, K);
+    const int K = std::min(tileBits, nEff), C = std::min(pinnedBits, K);
     qindex localSet = 0;
     for (int p = 0; p < nLocal; p++) localSet |= qindex(1) << state.layout[p];
     const int lookahead = 2048;
@@ -268,7 +292,7 @@ std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, 
             int best = -1; size_t bestGain = cur;
             for (int p = C; p < nLocal; p++) {
                 const int q = state.layout[p];
-                if (tile >> q & 1) continue;
+                if ((tile >> q & 1) || (exclude >> p & 1)) continue;
                 const size_t gain = hyquas::runnableGates(stageGates, remaining, tile | qindex(1) << q, lookahead).size();
                 if (gain > bestGain) { best = q; bestGain = gain; }
             }
@@ -277,7 +301,7 @@ std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, 
             cur = bestGain;
         }
         for (int p = 0; p < nLocal && bitCount(tile) < K; p++)   // pad with the lowest free physical bits (longer runs)
-            if (!(tile >> state.layout[p] & 1)) tile |= qindex(1) << state.layout[p];
+            if (!(tile >> state.layout[p] & 1) && !(exclude >> p & 1)) tile |= qindex(1) << state.layout[p];
         std::vector<int> take = hyquas::runnableGates(stageGates, remaining, tile, lookahead);
         if ((int)take.size() > maxGroupGates) take.resize(maxGroupGates);   // a prefix of a runnable set is runnable
         assert(!take.empty());
@@ -286,13 +310,13 @@ std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, 
         gg.relatedQubits = tile;
         gg.state = state;
         for (int gi : take) gg.gates.push_back(stageGates[gi]);
-        gg.predictedMs = Evaluator::getInstance()->perfPerGate(nLocal, gg.gates);
-        if (backendMode != 1 && nLocal >= 8) {
+        gg.predictedMs = Evaluator::getInstance()->perfPerGate(nEff, gg.gates);
+        if (backendMode != 1 && nEff >= 8) {
             // hybrid choice (the reference's AdvanceCompiler::run, src/compiler.cpp:250-278): price a dense launch for
             // the same frontier and keep whichever costs fewer predicted milliseconds per gate
-            GateGroup dense = denseCandidate(stageGates, remaining, state, nLocal);
+            GateGroup dense = denseCandidate(stageGates, remaining, state, nLocal, exclude);
             const bool pick = !dense.gates.empty() &&
-                (backendMode == 3 || nLocal < 10 ||
+                (backendMode == 3 || nEff < 10 ||
                  dense.predictedMs / dense.gates.size() < gg.predictedMs / gg.gates.size());
             if (pick) {
                 gg = std::move(dense);
@@ -321,15 +345,26 @@ Schedule Compiler::run() {
         lg.relatedQubits = stages[s].locals;
         if (s == 0) {
             // |0...0> is invariant under qubit relabelling: just declare the stage-0 locals to be at [0, numLocal)
+            // Stage-0 locals that leave later go to the TOP local positions, earliest leavers highest: the qubits coming in
+            // land on those same positions, so the traffic between local and global keeps using high positions (long
+            // contiguous runs on the wire, and for the nccl transport no local bit swaps at the first exchange).
             State st(numQubits);
-            int lo = 0, hi = numLocal;
-            for (int q = 0; q < numQubits; q++) {
-                const int p = (stages[s].locals >> q & 1) ? lo++ : hi++;
-                st.pos[q] = p; st.layout[p] = q;
-            }
+            std::vector<int> stay, leave;
+            std::vector<int> firstOut(numQubits, 1 << 30);
+            for (int q = 0; q < numQubits; q++)
+                for (size_t t = 1; t < stages.size(); t++)
+                    if ((stages[0].locals >> q & 1) && !(stages[t].locals >> q & 1)) { firstOut[q] = (int)t; break; }
+            for (int q = 0; q < numQubits; q++)
+                if (stages[0].locals >> q & 1) (firstOut[q] < (1 << 30) ? leave : stay).push_back(q);
+            std::stable_sort(leave.begin(), leave.end(), [&](int a, int b) { return firstOut[a] > firstOut[b]; });
+            int p = 0;
+            for (int q : stay) { st.pos[q] = p; st.layout[p] = q; p++; }
+            for (int q : leave) { st.pos[q] = p; st.layout[p] = q; p++; }
+            for (int q = 0; q < numQubits; q++)
+                if (!(stages[0].locals >> q & 1)) { st.pos[q] = p; st.layout[p] = q; p++; }
             state = st;
         } else {
-            lg.swap = hyquas::planSwap(state, stages[s].locals, numQubits, numLocal);
+            lg.swap = hyquas::planSwap(state, stages[s].locals, numQubits, numLocal, MyGlobalVars::swapAnyBit);
         }
         lg.state = state;
         schedule.localGroups.push_back(std::move(lg));
@@ -342,9 +377,10 @@ Schedule Compiler::run() {
     for (size_t s = 1; s < stages.size() && enableOverlap; s++) {
         LocalGroup& lg = schedule.localGroups[s];
         const int k = (int)lg.swap.localBit.size();
-        if (k == 0 || numLocal - k < 10) continue;
-        qindex lowSet = 0;
-        for (int p = 0; p < numLocal - k; p++) lowSet |= qindex(1) << lg.state.layout[p];
+        if (k == 0 || numLocal - k < 8) continue;
+        qindex lowSet = 0, exclude = 0;
+        for (int b : lg.swap.localBit) exclude |= qindex(1) << b;
+        for (int p = 0; p < numLocal; p++) if (!(exclude >> p & 1)) lowSet |= qindex(1) << lg.state.layout[p];
         std::vector<Gate>& prev = stages[s - 1].gates;
         std::vector<int> order(prev.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = (int)prev.size() - 1 - (int)i;   // scan from the end
@@ -352,7 +388,7 @@ Schedule Compiler::run() {
         std::sort(tail.begin(), tail.end());
         std::vector<Gate> tailGates;
         for (int gi : tail) tailGates.push_back(prev[gi]);
-        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal - k);
+        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
         const double commMs = Evaluator::getInstance()->perfSwap(numLocal, k);
         double used = 0;
         size_t first = cand.size();
@@ -374,7 +410,7 @@ Schedule Compiler::run() {
     }
     // pass 3: cut what is left of every stage into full groups
     for (size_t s = 0; s < stages.size(); s++)
-        schedule.localGroups[s].fullGroups = cutGroups(stages[s].gates, schedule.localGroups[s].state, numLocal);
+        schedule.localGroups[s].fullGroups = cutGroups(stages[s].gates, schedule.localGroups[s].state, numLocal, 0);
     schedule.finalState = state;
     return schedule;
 }

@@ -29,8 +29,8 @@ public:
 private:
     struct Stage { std::vector<Gate> gates; qindex locals; };
     std::vector<Stage> splitStages() const;
-    GateGroup denseCandidate(const std::vector<Gate>& gates, const std::vector<int>& remaining, const State& state, int numLocal) const;
-    std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal) const;
+    GateGroup denseCandidate(const std::vector<Gate>& gates, const std::vector<int>& remaining, const State& state, int numLocal, qindex exclude) const;
+    std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     int numQubits;
     int numLocal;
     std::vector<Gate> gates;
@@ -42,5 +42,5 @@ namespace hyquas {
 // non-diagonal targets?  Gates that cannot run block later gates they do not commute with.
 std::vector<int> runnableGates(const std::vector<Gate>& gates, const std::vector<int>& order, qindex tileSet, int cap);
 std::vector<int> runnableDense(const std::vector<Gate>& gates, const std::vector<int>& order, qindex qset, int cap);
-hyquas::SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal);
+hyquas::SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal, bool anyBit);
 }

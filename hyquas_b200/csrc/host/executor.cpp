@@ -16,13 +16,13 @@ Executor::Executor(std::vector<qComplex*> deviceStateVec_, int numQubits_, Sched
 // a (necessarily diagonal) target on a non-local bit selects d = m00 or m11 and the gate degenerates to
 // "multiply by d where the remaining local controls are 1": a scalar (GCC/GZZ/GII there), a one-qubit
 // diag(1,d) on the control (Z/U1/GOC there), or a controlled diag(1,d).
-bool Executor::lowerGate(const Gate& gate, const State& state, int numLocal, qindex highIndex, hq_gate& out) {
+bool Executor::lowerGate(const Gate& gate, const State& state, qindex fixedMask, qindex fixedValue, hq_gate& out) {
     int localCtl[2] = {-1, -1}, nCtl = 0;
     for (int c : {gate.controlQubit, gate.controlQubit2}) {
         if (c < 0) continue;
         const int pc = state.pos[c];
-        if (pc >= numLocal) {
-            if (!(highIndex >> (pc - numLocal) & 1)) return false;
+        if (fixedMask >> pc & 1) {
+            if (!(fixedValue >> pc & 1)) return false;
         } else {
             localCtl[nCtl++] = pc;
         }
@@ -30,9 +30,9 @@ bool Executor::lowerGate(const Gate& gate, const State& state, int numLocal, qin
     std::memset(&out, 0, sizeof(out));
     out.control = out.control2 = -1;
     const int pt = state.pos[gate.targetQubit];
-    if (pt >= numLocal) {
-        if (!gate.isDiagonal()) UNREACHABLE()   // the partitioner keeps non-diagonal targets local
-        const bool hi = highIndex >> (pt - numLocal) & 1;
+    if (fixedMask >> pt & 1) {
+        if (!gate.isDiagonal()) UNREACHABLE()   // the partitioner keeps non-diagonal targets on varying bits
+        const bool hi = fixedValue >> pt & 1;
         const qComplex d = gate.mat[hi][hi];
         if (d.x == 1.0 && d.y == 0.0) return false;
         if (nCtl == 0) {
@@ -55,24 +55,38 @@ bool Executor::lowerGate(const Gate& gate, const State& state, int numLocal, qin
     return true;
 }
 
+// Fixed (non-varying) physical bits of a launch: the rank bits [L, n) always; for a per-chunk launch also the swapped local
+// positions, holding the chunk number.
+static void fixedBits(int numQubits, const std::vector<int>& chunkBits, int chunk, qindex& mask, qindex& value) {
+    const int L = numQubits - MyGlobalVars::bit;
+    mask = ((qindex(1) << numQubits) - 1) & ~((qindex(1) << L) - 1);
+    value = qindex(MyMPI::rank) << L;
+    for (size_t i = 0; i < chunkBits.size(); i++) {
+        mask |= qindex(1) << chunkBits[i];
+        if (chunk >> i & 1) value |= qindex(1) << chunkBits[i];
+    }
+}
+
 static uint64_t physicalMask(const State& st, qindex logical, int numQubits) {
     uint64_t m = 0;
     for (int q = 0; q < numQubits; q++) if (logical >> q & 1) m |= 1ull << st.pos[q];
     return m;
 }
 
-static void preparePerGate(GateGroup& gg, int numQubits, int numLocal, int numChunks) {
-    const qindex rank = MyMPI::rank;
+static void preparePerGate(GateGroup& gg, int numQubits, const std::vector<int>& chunkBits) {
+    const int L = numQubits - MyGlobalVars::bit;
+    const qindex localMask = (qindex(1) << L) - 1;
     gg.tileMask = physicalMask(gg.state, gg.relatedQubits, numQubits);
-    for (int chunk = 0; chunk < numChunks; chunk++) {
-        const qindex high = numChunks > 1 ? ((rank * numChunks) | chunk) : rank;
+    for (int chunk = 0; chunk < (1 << chunkBits.size()); chunk++) {
+        qindex fmask, fvalue;
+        fixedBits(numQubits, chunkBits, chunk, fmask, fvalue);
         std::vector<hq_gate> lowered;
         for (const Gate& g : gg.gates) {
             hq_gate k;
-            if (Executor::lowerGate(g, gg.state, numLocal, high, k)) lowered.push_back(k);
+            if (Executor::lowerGate(g, gg.state, fmask, fvalue, k)) lowered.push_back(k);
         }
         hq_group_plan* plan = nullptr;
-        checkHq(hq_group_plan_create(numLocal, gg.tileMask, lowered.data(), (int)lowered.size(), &plan));
+        checkHq(hq_group_plan_create_ex(L, gg.tileMask, fmask & localMask, fvalue & localMask, lowered.data(), (int)lowered.size(), &plan));
         gg.plans.push_back(plan);
     }
 }
@@ -80,7 +94,7 @@ static void preparePerGate(GateGroup& gg, int numQubits, int numLocal, int numCh
 // Dense matrix of one block for the sub-state whose high index bits equal `high`: U = G_last ... G_1 acting on the
 // block's qubits (matrix bit i = i-th lowest physical position).  Role of GateGroup::initCPUMatrix
 // (src/schedule.cpp:578-702); gates with global controls/targets are resolved per shard by lowerGate.
-static std::vector<double> buildDenseMatrix(const DenseBlock& blk, const State& state, int numLocal, qindex high,
+static std::vector<double> buildDenseMatrix(const DenseBlock& blk, const State& state, qindex fmask, qindex fvalue,
                                             const std::vector<int>& positions) {
     const int m = (int)positions.size(), K = 1 << m;
     std::vector<std::complex<double>> U((size_t)K * K, 0.0);   // column-major: U[row + col * K]
@@ -90,7 +104,7 @@ static std::vector<double> buildDenseMatrix(const DenseBlock& blk, const State& 
     for (int i = 0; i < m; i++) bitOf[positions[i]] = i;
     for (const Gate& g : blk.gates) {
         hq_gate k;
-        if (!Executor::lowerGate(g, state, numLocal, high, k)) continue;
+        if (!Executor::lowerGate(g, state, fmask, fvalue, k)) continue;
         const std::complex<double> m00(k.mat[0], k.mat[1]), m01(k.mat[2], k.mat[3]), m10(k.mat[4], k.mat[5]), m11(k.mat[6], k.mat[7]);
         int cmask = 0;
         for (int c : {k.control, k.control2}) {
@@ -120,31 +134,34 @@ static std::vector<double> buildDenseMatrix(const DenseBlock& blk, const State& 
     return out;
 }
 
-static void prepareDense(GateGroup& gg, int numQubits, int numLocal, int numChunks) {
-    const qindex rank = MyMPI::rank;
-    for (int chunk = 0; chunk < numChunks; chunk++) {
-        const qindex high = numChunks > 1 ? ((rank * numChunks) | chunk) : rank;
+static void prepareDense(GateGroup& gg, int numQubits, const std::vector<int>& chunkBits) {
+    const int L = numQubits - MyGlobalVars::bit;
+    const qindex localMask = (qindex(1) << L) - 1;
+    for (int chunk = 0; chunk < (1 << chunkBits.size()); chunk++) {
+        qindex fmask, fvalue;
+        fixedBits(numQubits, chunkBits, chunk, fmask, fvalue);
         std::vector<int> mList, qpos;
         std::vector<double> allU;
         for (const DenseBlock& blk : gg.blocks) {
             std::vector<int> positions;
             for (int q = 0; q < numQubits; q++) if (blk.qubits >> q & 1) positions.push_back(gg.state.pos[q]);
             std::sort(positions.begin(), positions.end());
-            std::vector<double> U = buildDenseMatrix(blk, gg.state, numLocal, high, positions);
+            std::vector<double> U = buildDenseMatrix(blk, gg.state, fmask, fvalue, positions);
             mList.push_back((int)positions.size());
             qpos.insert(qpos.end(), positions.begin(), positions.end());
             allU.insert(allU.end(), U.begin(), U.end());
         }
         hq_dense_plan* plan = nullptr;
-        checkHq(hq_dense_plan_create(numLocal, (int)mList.size(), mList.data(), qpos.data(), allU.data(), &plan));
+        checkHq(hq_dense_plan_create_ex(L, fmask & localMask, fvalue & localMask, (int)mList.size(), mList.data(), qpos.data(),
+                                        allU.data(), &plan));
         gg.plans.push_back(plan);
     }
 }
 
-static void prepareGroup(GateGroup& gg, int numQubits, int numLocal, int numChunks) {
+static void prepareGroup(GateGroup& gg, int numQubits, const std::vector<int>& chunkBits) {
     if (!gg.plans.empty()) return;
-    if (gg.backend == Backend::BLAS) prepareDense(gg, numQubits, numLocal, numChunks);
-    else preparePerGate(gg, numQubits, numLocal, numChunks);
+    if (gg.backend == Backend::BLAS) prepareDense(gg, numQubits, chunkBits);
+    else preparePerGate(gg, numQubits, chunkBits);
 }
 
 void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
@@ -156,8 +173,8 @@ void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
             checkHq(hq_swap_plan_create(L, k, lg.swap.localBit.data(), lg.swap.globalBit.data(), &sp));
             lg.swapPlan = sp;
         }
-        for (auto& gg : lg.overlapGroups) prepareGroup(gg, numQubits, L - k, 1 << k);
-        for (auto& gg : lg.fullGroups) prepareGroup(gg, numQubits, L, 1);
+        for (auto& gg : lg.overlapGroups) prepareGroup(gg, numQubits, lg.swap.localBit);
+        for (auto& gg : lg.fullGroups) prepareGroup(gg, numQubits, {});
     }
 }
 
@@ -177,21 +194,12 @@ void Executor::release(Schedule& schedule) {
 }
 
 void Executor::applyGateGroup(GateGroup& gg, int chunk) {
-    const int L = numQubits - MyGlobalVars::bit;
     if (perGroupMs) checkHq(hq_timer_start());
     auto launch = [&](void* plan, qComplex* base) {
         if (gg.backend == Backend::BLAS) checkHq(hq_dense_plan_launch(static_cast<hq_dense_plan*>(plan), base, 0))
         else checkHq(hq_group_plan_launch(static_cast<hq_group_plan*>(plan), base, 0))
     };
-    if (chunk < 0) {
-        launch(gg.plans[0], deviceStateVec[0]);
-    } else {
-        const int nChunks = (int)gg.plans.size();
-        int k = 0;
-        while ((1 << k) < nChunks) k++;
-        qComplex* base = deviceStateVec[0] + ((qindex)chunk << (L - k));
-        launch(gg.plans[chunk], base);
-    }
+    launch(gg.plans[chunk < 0 ? 0 : chunk], deviceStateVec[0]);   // a per-chunk plan carries its chunk's fixed bits
     if (perGroupMs) {
         float ms = 0;
         checkHq(hq_timer_stop_ms(&ms));

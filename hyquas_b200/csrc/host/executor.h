@@ -18,9 +18,9 @@ public:
     std::vector<float>* perGroupMs = nullptr;   // when set: one CUDA-event timing per gate-group launch (MEASURE_STAGE)
     static void prepare(Schedule& schedule, int numQubits, bool hostOnly = false);   // build device plans (idempotent)
     static void release(Schedule& schedule);                  // destroy device plans
-    // Lower one logical gate for the sub-state whose physical index bits >= numLocal equal `highIndex`.
-    // Returns false when the gate acts as identity there.
-    static bool lowerGate(const Gate& gate, const State& state, int numLocal, qindex highIndex, hq_gate& out);
+    // Lower one logical gate for the sub-state whose physical index bits in `fixedMask` equal `fixedValue` (rank bits,
+    // plus the swapped positions for a per-chunk launch).  Returns false when the gate acts as identity there.
+    static bool lowerGate(const Gate& gate, const State& state, qindex fixedMask, qindex fixedValue, hq_gate& out);
 private:
     void applyGateGroup(GateGroup& gg, int chunk);
     void finalize();

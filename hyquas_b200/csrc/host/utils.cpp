@@ -13,6 +13,7 @@ int numGPUs = 1;
 int localGPUs = 1;
 int bit = 0;
 bool hostOnly = false;
+bool swapAnyBit = false;
 
 static int envInt(const char* key, int dflt) {
     const char* v = getenv(key);
@@ -32,11 +33,17 @@ void init() {
     checkHq(hq_device_info(name, sizeof(name), nullptr, nullptr));
     Logger::add("Local GPU: %d", localGPUs);
     Logger::add("[%d] %s", MyMPI::rank, name);
-    if (numGPUs > 1) hyquas::commInitFromEnv();
+    if (numGPUs > 1) {
+        hyquas::commInitFromEnv();
+        int any = 0;
+        checkHq(hq_swap_any_position(&any));
+        swapAnyBit = any != 0;
+    }
 }
 
 void initForTest(int worldSize, int rank) {
     hostOnly = true;
+    if (const char* e = getenv("HQ_TEST_SWAP_ANY")) swapAnyBit = atoi(e) != 0;
     numGPUs = worldSize;
     localGPUs = 1;
     bit = get_bit(worldSize);

@@ -46,6 +46,7 @@ namespace MyGlobalVars {
     extern int numGPUs;    // GPUs taking part in the simulation (= number of processes, one GPU each)
     extern int localGPUs;  // GPUs driven by this process: always 1
     extern int bit;        // log2(numGPUs) = number of global qubits
+    extern bool swapAnyBit; // swaps may trade ANY local position >= 3 (p2p transport); else only the top k positions
     extern bool hostOnly;  // set by initForTest(): no GPU bound, plans stay on the host
     void init();
     void initForTest(int worldSize, int rank);   // host-only: no GPU is touched (compiler / plan tests)

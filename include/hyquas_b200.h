@@ -79,6 +79,10 @@ typedef struct hq_group_plan hq_group_plan;
 int hq_group_tile_bits(void);
 int hq_group_min_run_bits(void);
 int hq_group_plan_create(int L, uint64_t tile_mask, const hq_gate* gates, int ngates, hq_group_plan** plan);
+/* _ex: the launch covers only the amplitudes whose fixed_mask bits equal fixed_value (one chunk of the state while the
+ * other chunks are still on the wire, src/executor.cpp:495-531 applyPerGateGroupSliced); gates must not touch fixed bits. */
+int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed_mask, uint64_t fixed_value, const hq_gate* gates, int ngates,
+                            hq_group_plan** plan);
 int hq_group_plan_launch(const hq_group_plan* plan, void* state, int on_comm_stream);
 int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* ops, int* grid, int* smem_bytes);
 int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes);   /* size of the uploaded device tables */
@@ -93,6 +97,8 @@ int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates,
  *      All matrices of one plan must fit in one tile: their qubits together with physical bits 0..2 span <= 12 bits. */
 typedef struct hq_dense_plan hq_dense_plan;
 int hq_dense_plan_create(int L, int nmat, const int* m_list, const int* qubit_pos, const double* u_colmajor, hq_dense_plan** plan);
+int hq_dense_plan_create_ex(int L, uint64_t fixed_mask, uint64_t fixed_value, int nmat, const int* m_list, const int* qubit_pos,
+                            const double* u_colmajor, hq_dense_plan** plan);
 int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int on_comm_stream);
 int hq_dense_plan_info(const hq_dense_plan* plan, int* tile_bits, int* smem_bytes, int* grid, double* flops_per_amp, int* table_bytes);
 int hq_dense_plan_destroy(hq_dense_plan* plan);
@@ -111,6 +117,9 @@ int hq_comm_info(int* world, int* rank);
 int hq_comm_destroy(void);
 int hq_comm_bcast_host(void* buf, size_t bytes, int root);           /* control plane of printState (small host buffers) */
 int hq_comm_allgather_host(const void* send, void* recv, size_t bytes_per_rank);
+int hq_swap_any_position(int* any);      /* 1: p2p transport, swapped local bits may be any positions >= 3; 0: top k only */
+int hq_swap_attach(void* state);         /* p2p: map every rank's state into this process (collective, untimed) */
+int hq_swap_detach(void);
 int hq_state_bitswap(void* state, int L, int npairs, const int* a, const int* b);   /* in-place local bit permutation */
 int hq_swap_plan_create(int L, int k, const int* local_bits, const int* global_bits, hq_swap_plan** plan);
 int hq_swap_begin(hq_swap_plan* plan, void* state);                  /* enqueue the whole exchange on the comm stream */

@@ -50,21 +50,27 @@ def run_rank(rank, world, port, text, out_path, env):
             for i in range(npairs.value):
                 idx = swap_bits(idx, pa[i], pb[i])
             shard = shard[idx]                       # product of disjoint transpositions = involution
-            assert [lb[i] for i in range(kk)] == list(range(L - kk, L))
-            chunks = shard.reshape(1 << kk, -1)
+            lbits = [lb[i] for i in range(kk)]
+            if os.environ.get("HQ_TEST_SWAP_ANY", "0") != "1":
+                assert lbits == list(range(L - kk, L))          # nccl transport: contiguous chunks
+            allidx = np.arange(1 << L, dtype=np.int64)
+            chunk_of = np.zeros(1 << L, dtype=np.int64)
+            for i, b in enumerate(lbits):
+                chunk_of |= ((allidx >> b) & 1) << i
             myc = sum(((rank >> gb[i]) & 1) << i for i in range(kk))
             for xr in range(1, 1 << kk):
                 ch = myc ^ xr
                 peer = rank
                 for i in range(kk):
                     peer = (peer & ~(1 << gb[i])) | (((ch >> i) & 1) << gb[i])
-                send = torch.from_numpy(np.ascontiguousarray(chunks[ch]).view(np.float64).copy())
+                sel = chunk_of == ch                        # both sides enumerate the pair in order of the other L-k bits
+                send = torch.from_numpy(np.ascontiguousarray(shard[sel]).view(np.float64).copy())
                 recv = torch.empty_like(send)
                 ops = [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, recv, peer)]
                 for r in dist.batch_isend_irecv(ops):
                     r.wait()
-                chunks[ch] = recv.numpy().view(np.complex128)
-            shard = np.ascontiguousarray(chunks.reshape(-1))
+                shard[sel] = recv.numpy().view(np.complex128)
+            shard = np.ascontiguousarray(shard)
             for xr in range(1 << kk):                # arrival order of the product path: own chunk first
                 check(lib.hq_debug_stage_emulate(c._h, s, 0, myc ^ xr, shard.ctypes.data))
         check(lib.hq_debug_stage_emulate(c._h, s, 1, 0, shard.ctypes.data))

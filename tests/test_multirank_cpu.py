@@ -30,12 +30,14 @@ def _run(world, text, env=None):
     return np.load(out), stages, overlap
 
 
-@pytest.mark.parametrize("world,name", [(2, "qft_14"), (2, "supremacy_14"), (2, "qaoa_14"), (2, "adder_14"),
+@pytest.mark.parametrize("any_bit", ["0", "1"])
+@pytest.mark.parametrize("world,name", [(2, "qft_14"), (2, "supremacy_14"), (2, "adder_14"),
                                         (4, "quantum_volume_14"), (4, "hidden_shift_14"), (4, "basis_change_14"),
                                         (4, "bv_15")])
-def test_sharded_schedule_matches_oracle(world, name):
+def test_sharded_schedule_matches_oracle(world, name, any_bit):
+    """any_bit=0: swaps trade the top k local positions (nccl transport); 1: any position >= 5 (p2p transport)."""
     text = C.generate(name)
-    got, stages, _ = _run(world, text)
+    got, stages, _ = _run(world, text, env={"HQ_TEST_SWAP_ANY": any_bit})
     n, gates = O.parse_qasm(text)
     want = O.simulate(n, gates)
     assert np.max(np.abs(got - want)) <= 1e-10
@@ -46,20 +48,21 @@ def test_random_circuit_needs_several_exchanges():
     names = ["h", "x", "y", "z", "s", "sdg", "t", "tdg", "rx", "ry", "rz", "u1", "u3", "cx", "cy", "cz", "crx", "cry",
              "crz", "cu1", "ccx"]
     text = C.random_circuit(14, 400, seed=21, names=names)
-    got, stages, overlap = _run(4, text)
+    got, stages, overlap = _run(4, text, env={"HQ_TEST_SWAP_ANY": "1"})
     n, gates = O.parse_qasm(text)
     assert np.max(np.abs(got - O.simulate(n, gates))) <= 1e-10
     assert stages >= 3          # every qubit is a non-diagonal target many times: the layout must keep rotating
 
 
+@pytest.mark.parametrize("any_bit", ["0", "1"])
 @pytest.mark.parametrize("world,name", [(2, "supremacy_14"), (4, "qaoa_14"), (4, "quantum_volume_14"), (2, "adder_14")])
-def test_overlap_groups_present_and_optional(world, name):
+def test_overlap_groups_present_and_optional(world, name, any_bit):
     """Per-chunk (overlap) groups: forced on with a huge slack (at 14 qubits the predicted exchange is too short to hide
     anything), and switched off -- same amplitudes either way."""
     text = C.generate(name)
     n, gates = O.parse_qasm(text)
     want = O.simulate(n, gates)
-    got, _, overlap = _run(world, text, env={"HQ_OVERLAP_SLACK": "1e9"})
+    got, _, overlap = _run(world, text, env={"HQ_OVERLAP_SLACK": "1e9", "HQ_TEST_SWAP_ANY": any_bit})
     assert overlap >= 1 and np.max(np.abs(got - want)) <= 1e-10
-    got, _, overlap = _run(world, text, env={"HQ_ENABLE_OVERLAP": "0"})
+    got, _, overlap = _run(world, text, env={"HQ_ENABLE_OVERLAP": "0", "HQ_TEST_SWAP_ANY": any_bit})
     assert overlap == 0 and np.max(np.abs(got - want)) <= 1e-10
