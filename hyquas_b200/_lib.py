@@ -79,6 +79,7 @@ _SIGS = {
     "hq_swap_detach": (_c.c_int, []),
     "hq_state_bitswap": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int)]),
     "hq_swap_plan_create": (_c.c_int, [_c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_void_p)]),
+    "hq_swap_plan_set_overlap": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "hq_swap_begin": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "hq_swap_wait_chunk": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_swap_end": (_c.c_int, [_c.c_void_p]),

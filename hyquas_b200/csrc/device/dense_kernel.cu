@@ -127,12 +127,15 @@ __device__ __forceinline__ void dense_block(double2* tile, const double2* __rest
 
 // MAXM = 4: every matrix of the launch has <= 4 qubits (16 accumulator doubles per thread, 3 CTAs per SM);
 // MAXM = 6: general (32 accumulator doubles, 2 CTAs per SM).
-template <int MAXM>
-__global__ void __launch_bounds__(DENSE_THREADS, MAXM <= 4 ? 3 : 2) dense_kernel(const __grid_constant__ DenseParams P) {
+// DB: two tile buffers per CTA (one CTA per SM); the gather of tile i+1 is issued BEFORE tile i is computed, so HBM
+// reads run under the tensor-core phase of the same CTA by construction.  (With one buffer and 2-3 CTAs per SM the CTAs fall
+// into lock step -- all loading, then all computing -- and the DMMA pipe idles a third of the time: ncu, profiles/r01_s10.)
+template <int MAXM, bool DB>
+__global__ void __launch_bounds__(DENSE_THREADS, DB ? 1 : (MAXM <= 4 ? 3 : 2)) dense_kernel(const __grid_constant__ DenseParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int TILE = 1 << P.Kt;
-    double2* tile = reinterpret_cast<double2*>(smem_raw);
-    double2* u_s = tile + TILE;
+    double2* tile0 = reinterpret_cast<double2*>(smem_raw);
+    double2* u_s = tile0 + (DB ? 2 : 1) * TILE;
     uint16_t* tab_s = reinterpret_cast<uint16_t*>(u_s + P.u_total);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -151,16 +154,39 @@ __global__ void __launch_bounds__(DENSE_THREADS, MAXM <= 4 ? 3 : 2) dense_kernel
         }
     const uint32_t s_low = (uint32_t)tid ^ f_low;
     const int per_thread = TILE / DENSE_THREADS;
-    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t tile0_s = (uint32_t)__cvta_generic_to_shared(tile0);
     __syncthreads();
 
-    for (uint64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+    auto tile_base = [&](uint64_t t) {
         uint64_t base = P.fixed_base;
         for (int s = 0; s < P.nseg; ++s) base |= ((t >> P.seg_src[s]) & P.seg_mask[s]) << P.seg_shift[s];
-        double2* gbase = P.state + base + g_low;
-        for (int i = 0; i < per_thread; ++i) cp_async16(tile_s + ((s_low ^ P.f_high[i]) << 4), gbase + P.g_high[i]);
-        cp_async_wait_all();
+        return P.state + base + g_low;
+    };
+    auto gather = [&](double2* gbase, int buf) {
+        const uint32_t dst = tile0_s + (uint32_t)buf * (uint32_t)TILE * 16u;
+        for (int i = 0; i < per_thread; ++i) cp_async16(dst + ((s_low ^ P.f_high[i]) << 4), gbase + P.g_high[i]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint64_t t = blockIdx.x;
+    int cur = 0;
+    double2* gbase = nullptr;
+    if (t < P.ntiles) {
+        gbase = tile_base(t);
+        gather(gbase, 0);
+    }
+    for (; t < P.ntiles; t += gridDim.x) {
+        const uint64_t tn = t + gridDim.x;
+        double2* gnext = nullptr;
+        if (DB && tn < P.ntiles) {   // prefetch the next tile into the other buffer, then wait for the current one only
+            gnext = tile_base(tn);
+            gather(gnext, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            cp_async_wait_all();
+        }
         __syncthreads();
+        double2* tile = tile0 + (size_t)cur * TILE;
 
         for (int mi = 0; mi < P.nmat; ++mi) {
             const DenseMatDesc d = P.mats[mi];
@@ -184,7 +210,18 @@ __global__ void __launch_bounds__(DENSE_THREADS, MAXM <= 4 ? 3 : 2) dense_kernel
         }
 
         for (int i = 0; i < per_thread; ++i) gbase[P.g_high[i]] = tile[s_low ^ P.f_high[i]];
-        __syncthreads();
+        if (DB) {
+            gbase = gnext;
+            cur ^= 1;
+            // the buffer just stored is refilled by the NEXT iteration's prefetch: every thread must be done reading it
+            __syncthreads();
+        } else {
+            __syncthreads();
+            if (tn < P.ntiles) {
+                gbase = tile_base(tn);
+                gather(gbase, 0);
+            }
+        }
     }
 }
 
@@ -425,20 +462,30 @@ extern "C" int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int 
     HQ_REQUIRE(plan && state, "null plan or state");
     HQ_REQUIRE(rt().ready && plan->dev_blob, "dense plan was created without a bound GPU (call hq_init first)");
     static bool attr_set = false;
+    static bool want_db = true;
     if (!attr_set) {
-        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HQ_CUDA(cudaFuncSetAttribute(dense_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (const char* e = getenv("HQ_DENSE_DB")) want_db = atoi(e) != 0;
         attr_set = true;
     }
     int maxm = 0;
     for (int i = 0; i < plan->p.nmat; ++i) maxm = std::max(maxm, plan->p.mats[i].m);
-    auto kern = maxm <= 4 ? dense_kernel<4> : dense_kernel<6>;
+    const size_t smem_db = plan->smem + ((size_t)16 << plan->Kt);
+    const bool db = want_db && smem_db <= 227 * 1024;
+    auto kern = db ? (maxm <= 4 ? dense_kernel<4, true> : dense_kernel<6, true>) : (maxm <= 4 ? dense_kernel<4, false> : dense_kernel<6, false>);
+    const size_t smem = db ? smem_db : plan->smem;
     int nb = 0;
-    HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, DENSE_THREADS, plan->smem));
+    HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, DENSE_THREADS, smem));
     DenseParams p = plan->p;
     p.state = static_cast<double2*>(state);
-    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * std::max(1, nb) - rt().reserved_ctas));
-    kern<<<plan->grid, DENSE_THREADS, plan->smem, on_comm_stream ? rt().comm : rt().compute>>>(p);
+    // a co-resident swap kernel (16K registers per CTA, no shared memory) fits next to the one double-buffered CTA of an SM;
+    // the single-buffer shape fills the register file and must leave slots free instead
+    const int reserve = db ? 0 : rt().reserved_ctas;
+    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * std::max(1, nb) - reserve));
+    kern<<<plan->grid, DENSE_THREADS, smem, on_comm_stream ? rt().comm : rt().compute>>>(p);
     HQ_CUDA(cudaGetLastError());
     return HQ_OK;
 }

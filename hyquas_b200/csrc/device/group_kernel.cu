@@ -89,7 +89,9 @@ __device__ __forceinline__ void op_diag_t(const DevOp& o, uint64_t phys) {
 }
 
 // A run of diagonal gates none of which touches a register bit: every amplitude of the thread gets the same factor.
-__device__ __forceinline__ void op_diag_run(const DevOp* entries, int n, uint64_t phys) {
+// With creg != 0 the factor applies only to the amplitudes whose register-index bits creg are all 1: every diagonal gate
+// with one operand on a register bit and the others elsewhere (the cu1 ladder of a QFT, CZ / CRZ fans) joins such a run.
+__device__ __forceinline__ void op_diag_run(const DevOp* entries, int n, uint64_t phys, uint32_t creg) {
     double fr = 1.0, fi = 0.0;
     bool any = false;
     for (int e = 0; e < n; ++e) {
@@ -103,7 +105,10 @@ __device__ __forceinline__ void op_diag_run(const DevOp* entries, int n, uint64_
         fr = nr;
         any = true;
     }
-    if (any) hq_cmul_all(fr, fi);
+    if (!any) return;
+    if (creg == 0) hq_cmul_all(fr, fi);
+    else if ((creg & (creg - 1)) == 0) hq_cmul_bit(fr, fi, 31 - __clz(creg));
+    else hq_cmul_masked(fr, fi, creg);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
                 const DevOp& o = ops_s[op];
                 const uint32_t code = o.code;
                 if (code == CODE_DIAG_RUN) {
-                    op_diag_run(&o + 1, (int)o.aux, phys);
+                    op_diag_run(&o + 1, (int)o.aux, phys, o.creg);
                     op += (int)o.aux;
                     continue;
                 }
@@ -359,6 +364,24 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         // lower the round's gates first: the thread-bit assignment below wants to know which tile bits act as
         // thread-level predicates
         std::vector<DevOp> body, run;
+        // creg -> diagonal gates waiting to be merged into one run: (run entry, the op as it would be emitted on its own)
+        std::map<uint32_t, std::vector<std::pair<DevOp, DevOp>>> pending;
+        auto flush = [&](uint32_t touching) {             // emit every pending run that involves register bits `touching`
+            for (auto it = pending.begin(); it != pending.end();) {
+                if (!(it->first & touching)) { ++it; continue; }
+                if (it->second.size() == 1) {
+                    body.push_back(it->second[0].second);
+                } else {
+                    DevOp hdr{};
+                    hdr.code = CODE_DIAG_RUN;
+                    hdr.aux = (uint32_t)it->second.size();
+                    hdr.creg = it->first;
+                    body.push_back(hdr);
+                    for (auto& pr : it->second) body.push_back(pr.first);
+                }
+                it = pending.erase(it);
+            }
+        };
         uint32_t predicate_tile_bits = 0;
         for (int gi : rd.gates) {
             const HostGate& h = hg[gi];
@@ -384,15 +407,30 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                     const uint32_t tbit = reg_of_tile[phys_to_tile[tgt]];
                     const bool zflip = d0one && h.m[6] == -1.0 && h.m[7] == 0.0;
                     o.code = op_code(zflip ? OP_ZFLIP : OP_DIAG_R, tbit, cbc);
-                    body.push_back(o);
+                    if (d0one && o.creg == 0) {
+                        // diag(1,d) whose ONLY register operand is tbit (T on a register qubit, the cu1 ladder of a QFT,
+                        // CZ fans): "multiply by d where tbit = 1 and the other operands are 1".  Consecutive ones on the
+                        // same register bit merge into a single run: one factor per thread, one multiply pass.
+                        DevOp e = o;
+                        e.code = CODE_DIAG_T;
+                        e.creg = 1u << tbit;
+                        e.tphys = 0;   // scalar d1, gated by cphys
+                        pending[e.creg].push_back({e, o});
+                    } else {
+                        body.push_back(o);
+                    }
                 } else {
                     o.tphys = tgt >= 0 ? 1ull << tgt : 0;
                     if (tgt >= 0 && phys_to_tile[tgt] >= 0) predicate_tile_bits |= 1u << phys_to_tile[tgt];
                     o.code = CODE_DIAG_T;
-                    (o.creg == 0 ? run : body).push_back(o);   // no register bit involved: joins the diagonal run
+                    // no register bit involved: joins the round's diagonal run; register bits only as controls: joins the
+                    // pending run of that control set (flushed before the next non-diagonal gate on one of those bits)
+                    if (o.creg == 0) run.push_back(o);
+                    else pending[o.creg].push_back({o, o});
                 }
             } else {
                 const uint32_t tbit = reg_of_tile[phys_to_tile[tgt]];
+                flush(1u << tbit);   // diagonal runs controlled by this register bit must act before it is mixed
                 const bool generic_only = h.kind == OP_GEN || h.kind == OP_REAL || h.kind == OP_RXL || h.kind == OP_YL;
                 const uint32_t cb = (generic_only && cbc != 0) ? CBC_GENERIC : cbc;
                 if (h.kind == OP_SWAP || h.kind == OP_YL) {
@@ -460,6 +498,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             tb[(size_t)(2 * r + 1) * NT + t] = (uint16_t)swz(j);
             gt[(size_t)r * NT + t] = pdep64(j, tile_mask);
         }
+        flush(~0u);
         for (DevOp& o : body)   // body index for the kernel's single indexed branch
             if (o.code < CODE_DIAG_T) o.flags |= (uint32_t)HQ_OP_BODY_INDEX[o.code] << 8;
         d.op_begin = (int)dops.size();

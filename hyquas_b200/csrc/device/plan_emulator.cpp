@@ -36,7 +36,8 @@ int applyOp(Amp* a, const DevOp* op, uint64_t phys) {
             fi = fi * dr + fr * di;
             fr = nr;
         }
-        for (int i = 0; i < R; ++i) cmul(a[i], fr, fi);
+        for (int i = 0; i < R; ++i)
+            if ((i & o.creg) == o.creg) cmul(a[i], fr, fi);
         return (int)o.aux;
     }
     if ((phys & o.cphys) != o.cphys) return 0;

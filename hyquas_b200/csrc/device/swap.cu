@@ -146,17 +146,19 @@ struct XchgParams {
     uint8_t seg_shift[8], seg_src[8];
     uint64_t seg_mask[8];
 };
-// Few CTAs (they must leave room for the gate groups that run under the exchange), so every thread keeps XCHG_UNROLL
-// remote loads in flight to cover the NVLink round trip.
-constexpr int XCHG_UNROLL = 8;
-__global__ void __launch_bounds__(512) xchg_kernel(const __grid_constant__ XchgParams P) {
+// Two shapes of the same kernel.  <8, 512>: nothing runs under this exchange -- 32 fat CTAs, 8 remote loads in flight per
+// thread.  <4, 256, 4>: gate groups run under the exchange -- many small CTAs (<= 64 registers, 16K registers per CTA) that fit
+// NEXT to the compute CTAs on an SM (the compute grids are shrunk by `reserved_ctas` slots to make that room), so neither
+// kernel has to wait for the other to drain.
+template <int UNROLL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) xchg_kernel(const __grid_constant__ XchgParams P) {
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t i0 = tid; i0 < P.count; i0 += nthreads * XCHG_UNROLL) {
-        double2 *pm[XCHG_UNROLL], *pp[XCHG_UNROLL];
-        double2 a[XCHG_UNROLL], b[XCHG_UNROLL];
+    for (uint64_t i0 = tid; i0 < P.count; i0 += nthreads * UNROLL) {
+        double2 *pm[UNROLL], *pp[UNROLL];
+        double2 a[UNROLL], b[UNROLL];
 #pragma unroll
-        for (int u = 0; u < XCHG_UNROLL; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
             const uint64_t i = i0 + (uint64_t)u * nthreads;   // consecutive threads stay on consecutive amplitudes
             const uint64_t z = P.z0 + (i < P.count ? i : i0);
             uint64_t idx = 0;
@@ -166,11 +168,11 @@ __global__ void __launch_bounds__(512) xchg_kernel(const __grid_constant__ XchgP
             pp[u] = P.peer + (idx | P.peer_bits);
         }
 #pragma unroll
-        for (int u = 0; u < XCHG_UNROLL; ++u) b[u] = *pp[u];
+        for (int u = 0; u < UNROLL; ++u) b[u] = *pp[u];
 #pragma unroll
-        for (int u = 0; u < XCHG_UNROLL; ++u) a[u] = *pm[u];
+        for (int u = 0; u < UNROLL; ++u) a[u] = *pm[u];
 #pragma unroll
-        for (int u = 0; u < XCHG_UNROLL; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
             if (i0 + (uint64_t)u * nthreads < P.count) {
                 *pm[u] = b[u];
                 *pp[u] = a[u];
@@ -196,6 +198,7 @@ struct hq_swap_plan {
     cudaEvent_t compute_done = nullptr, all_done = nullptr;
     int next = 0;
     bool top = false;                 // swapped local bits are the top k positions (contiguous chunks)
+    bool coresident = false;          // gate groups run under this exchange (hq_swap_plan_set_overlap)
     std::vector<int> local_bits;
     hq::XchgParams xp{};              // p2p: segment tables (z -> index with holes at the swapped positions)
     uint64_t chunk_bits(int c) const {
@@ -444,6 +447,13 @@ extern "C" int hq_swap_plan_create(int L, int k, const int* local_bits, const in
     return HQ_OK;
 }
 
+// Tell the plan whether per-chunk gate groups will run while it is in flight (chooses the exchange kernel's shape).
+extern "C" int hq_swap_plan_set_overlap(hq_swap_plan* p, int groups_under_exchange) {
+    HQ_REQUIRE(p != nullptr, "null swap plan");
+    p->coresident = groups_under_exchange > 0;
+    return HQ_OK;
+}
+
 extern "C" int hq_swap_plan_destroy(hq_swap_plan* p) {
     if (!p) return HQ_OK;
     for (auto& e : p->landed) cudaEventDestroy(e);
@@ -467,9 +477,9 @@ extern "C" int hq_swap_begin(hq_swap_plan* p, void* state_v) {
         HQ_CUDA(cudaEventRecord(p->landed[p->myc], comm));   // nobody else touches the chunk that stays
         // every rank's earlier compute must be finished before anybody reads or writes its memory
         HQ_NCCL(c.AllReduce(c.sync_buf, c.sync_buf + 1, 1, ncclDouble, ncclSum, c.comm, comm));
-        int ctas = 32;
-        if (const char* e = getenv("HQ_SWAP_CTAS")) ctas = std::max(1, atoi(e));
-        rt().reserved_ctas = ctas;   // gate-group launches under the exchange size their grids around these CTAs
+        int ctas = p->coresident ? 96 : 32;
+        if (const char* e = getenv(p->coresident ? "HQ_SWAP_CTAS_OVERLAP" : "HQ_SWAP_CTAS")) ctas = std::max(1, atoi(e));
+        rt().reserved_ctas = p->coresident ? ctas : 0;   // gate-group launches under the exchange leave these CTA slots free
         for (int xr = 1; xr < (1 << p->k); ++xr) {
             const int ch = p->myc ^ xr, peer = p->peer[xr];
             XchgParams xp = p->xp;
@@ -479,7 +489,8 @@ extern "C" int hq_swap_begin(hq_swap_plan* p, void* state_v) {
             xp.peer_bits = p->chunk_bits(p->myc);
             xp.count = chunk_amps / 2;
             xp.z0 = c.rank < peer ? 0 : chunk_amps / 2;
-            xchg_kernel<<<ctas, 512, 0, comm>>>(xp);
+            if (p->coresident) xchg_kernel<4, 256, 4><<<ctas, 256, 0, comm>>>(xp);
+            else xchg_kernel<8, 512, 1><<<ctas, 512, 0, comm>>>(xp);
             HQ_CUDA(cudaGetLastError());
             // pairwise barrier: the chunk is complete once BOTH halves are done
             HQ_NCCL(c.api.GroupStart());

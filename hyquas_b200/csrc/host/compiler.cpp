@@ -124,7 +124,13 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
     overlapSlack = 1.0;
     if (const char* e = getenv("HQ_OVERLAP_SLACK")) overlapSlack = atof(e);
     enableOverlap = true;
+    overlapSplit = false;
     if (const char* e = getenv("HQ_ENABLE_OVERLAP")) enableOverlap = atoi(e) != 0;
+    if (const char* e = getenv("HQ_OVERLAP_MODE")) {
+        const std::string v = e;
+        if (v == "off") enableOverlap = false;
+        overlapSplit = v == "split";
+    }
     maxGroupGates = 384;
     if (const char* e = getenv("HQ_MAX_GROUP_GATES")) maxGroupGates = std::max(1, atoi(e));
 }
@@ -370,10 +376,11 @@ Schedule Compiler::run() {
         schedule.localGroups.push_back(std::move(lg));
     }
     // pass 2: work to hide the exchange behind.  The stage split is greedy, so the head of stage s always needs the
-    // incoming qubits; what CAN run while chunks are still on the wire is the tail of stage s-1: gates that commute
-    // to the end of that stage and whose non-diagonal targets sit below the k swapped positions in the NEW layout.
-    // They are deferred past the swap and run per landed chunk (the reference's moveToNext + overlapGroups,
-    // src/compiler.cpp:34-68, src/executor.cpp:41-47).  Only as many groups as the predicted exchange time hides.
+    // incoming qubits; what CAN run while chunks are still on the wire is the tail of stage s-1 (the reference's moveToNext
+    // + overlapGroups, src/compiler.cpp:34-68, src/executor.cpp:41-47).  Only WHOLE trailing groups of stage s-1 are
+    // deferred past the swap -- the sweep count stays what it was, those sweeps merely move under the exchange -- and only
+    // as many as the predicted exchange time hides.  A group qualifies when every non-diagonal target avoids the swapped
+    // positions in the NEW layout and it still fits one launch there.
     for (size_t s = 1; s < stages.size() && enableOverlap; s++) {
         LocalGroup& lg = schedule.localGroups[s];
         const int k = (int)lg.swap.localBit.size();
@@ -382,26 +389,47 @@ Schedule Compiler::run() {
         for (int b : lg.swap.localBit) exclude |= qindex(1) << b;
         for (int p = 0; p < numLocal; p++) if (!(exclude >> p & 1)) lowSet |= qindex(1) << lg.state.layout[p];
         std::vector<Gate>& prev = stages[s - 1].gates;
-        std::vector<int> order(prev.size());
-        for (size_t i = 0; i < order.size(); i++) order[i] = (int)prev.size() - 1 - (int)i;   // scan from the end
-        std::vector<int> tail = hyquas::runnableGates(prev, order, lowSet, 1 << 30);
-        std::sort(tail.begin(), tail.end());
-        std::vector<Gate> tailGates;
-        for (int gi : tail) tailGates.push_back(prev[gi]);
-        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
         const double commMs = Evaluator::getInstance()->perfSwap(numLocal, k);
         double used = 0;
-        size_t first = cand.size();
-        while (first > 0) {   // longest suffix of the candidate groups that fits under the exchange
-            const double ms = cand[first - 1].predictedMs * (1 << k);   // predictedMs is per chunk
+        std::vector<int> ids;
+        if (overlapSplit) {
+            // "split" variant (HQ_OVERLAP_MODE=split): defer the maximal suffix-closed set of gates that avoid the swapped
+            // positions, re-cut into per-chunk groups.  Hides more, but the re-cut may add sweeps to the schedule.
+            std::vector<int> order(prev.size());
+            for (size_t i = 0; i < order.size(); i++) order[i] = (int)prev.size() - 1 - (int)i;   // scan from the end
+            std::vector<int> tail = hyquas::runnableGates(prev, order, lowSet, 1 << 30);
+            std::sort(tail.begin(), tail.end());
+            std::vector<Gate> tailGates;
+            for (int gi : tail) tailGates.push_back(prev[gi]);
+            std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
+            size_t first = cand.size();
+            while (first > 0) {   // longest suffix of the candidate groups that fits under the exchange
+                const double ms = cand[first - 1].predictedMs * (1 << k);
+                if (used + ms > commMs * overlapSlack) break;
+                used += ms;
+                first--;
+            }
+            for (size_t i = first; i < cand.size(); i++) {
+                for (auto& g : cand[i].gates) ids.push_back(g.gateID);
+                lg.overlapGroups.push_back(cand[i]);
+            }
+        }
+        std::vector<GateGroup> prevGroups;
+        if (!overlapSplit) prevGroups = cutGroups(prev, schedule.localGroups[s - 1].state, numLocal, 0);
+        while (!prevGroups.empty()) {
+            const GateGroup& last = prevGroups.back();
+            bool ok = true;
+            for (const Gate& g : last.gates)
+                if (!g.isDiagonal() && !(lowSet >> g.targetQubit & 1)) { ok = false; break; }
+            if (!ok) break;
+            std::vector<GateGroup> recut = cutGroups(last.gates, lg.state, numLocal, exclude);
+            if (recut.size() != 1) break;
+            const double ms = recut[0].predictedMs * (1 << k);   // predictedMs is per chunk
             if (used + ms > commMs * overlapSlack) break;
             used += ms;
-            first--;
-        }
-        std::vector<int> ids;
-        for (size_t i = first; i < cand.size(); i++) {
-            for (auto& g : cand[i].gates) ids.push_back(g.gateID);
-            lg.overlapGroups.push_back(cand[i]);
+            for (const Gate& g : last.gates) ids.push_back(g.gateID);
+            lg.overlapGroups.insert(lg.overlapGroups.begin(), recut[0]);
+            prevGroups.pop_back();
         }
         std::sort(ids.begin(), ids.end());
         std::vector<Gate> rest;

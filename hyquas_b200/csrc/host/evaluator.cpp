@@ -25,9 +25,10 @@ Evaluator::Evaluator() {
     auto set = [&](GateType t, double ms30) { gateNs[int(t)] = ms30; };
     set(GateType::H, 0.35); set(GateType::RY, 0.37); set(GateType::RX, 0.50);
     set(GateType::U2, 0.75); set(GateType::U3, 0.75);
-    set(GateType::T, 0.33); set(GateType::TDG, 0.33); set(GateType::S, 0.33); set(GateType::SDG, 0.33); set(GateType::U1, 0.33);
-    set(GateType::RZ, 0.45); set(GateType::Z, 0.20); set(GateType::X, 0.37); set(GateType::Y, 0.37);
-    set(GateType::CZ, 0.20); set(GateType::CU1, 0.27); set(GateType::CRZ, 0.35);
+    // diag(1,d) gates merge into per-register-bit diagonal runs (one factor per thread): ~0.1 ms each
+    set(GateType::T, 0.11); set(GateType::TDG, 0.11); set(GateType::S, 0.11); set(GateType::SDG, 0.11); set(GateType::U1, 0.11);
+    set(GateType::RZ, 0.45); set(GateType::Z, 0.11); set(GateType::X, 0.37); set(GateType::Y, 0.37);
+    set(GateType::CZ, 0.13); set(GateType::CU1, 0.13); set(GateType::CRZ, 0.35);
     set(GateType::CNOT, 0.27); set(GateType::CY, 0.30); set(GateType::CCX, 0.20);
     set(GateType::CRX, 0.45); set(GateType::CRY, 0.40);
     const double dense[8] = {2.7, 2.7, 2.7, 2.7, 5.4, 9.7, 20.1, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)

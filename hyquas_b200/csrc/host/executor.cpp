@@ -171,6 +171,7 @@ void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
         if (k > 0 && !lg.swapPlan && hostOnly == false) {
             hq_swap_plan* sp = nullptr;
             checkHq(hq_swap_plan_create(L, k, lg.swap.localBit.data(), lg.swap.globalBit.data(), &sp));
+            checkHq(hq_swap_plan_set_overlap(sp, (int)lg.overlapGroups.size()));
             lg.swapPlan = sp;
         }
         for (auto& gg : lg.overlapGroups) prepareGroup(gg, numQubits, lg.swap.localBit);

@@ -122,6 +122,7 @@ int hq_swap_attach(void* state);         /* p2p: map every rank's state into thi
 int hq_swap_detach(void);
 int hq_state_bitswap(void* state, int L, int npairs, const int* a, const int* b);   /* in-place local bit permutation */
 int hq_swap_plan_create(int L, int k, const int* local_bits, const int* global_bits, hq_swap_plan** plan);
+int hq_swap_plan_set_overlap(hq_swap_plan* plan, int groups_under_exchange);   /* picks the exchange kernel's shape */
 int hq_swap_begin(hq_swap_plan* plan, void* state);                  /* enqueue the whole exchange on the comm stream */
 int hq_swap_wait_chunk(hq_swap_plan* plan, int* chunk);              /* compute stream waits for the next landed chunk */
 int hq_swap_end(hq_swap_plan* plan);

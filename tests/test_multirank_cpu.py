@@ -62,7 +62,7 @@ def test_overlap_groups_present_and_optional(world, name, any_bit):
     text = C.generate(name)
     n, gates = O.parse_qasm(text)
     want = O.simulate(n, gates)
-    got, _, overlap = _run(world, text, env={"HQ_OVERLAP_SLACK": "1e9", "HQ_TEST_SWAP_ANY": any_bit})
+    got, _, overlap = _run(world, text, env={"HQ_OVERLAP_SLACK": "1e9", "HQ_OVERLAP_MODE": "split", "HQ_TEST_SWAP_ANY": any_bit})
     assert overlap >= 1 and np.max(np.abs(got - want)) <= 1e-10
     got, _, overlap = _run(world, text, env={"HQ_ENABLE_OVERLAP": "0", "HQ_TEST_SWAP_ANY": any_bit})
     assert overlap == 0 and np.max(np.abs(got - want)) <= 1e-10

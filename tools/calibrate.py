@@ -16,8 +16,8 @@ import sys
 GATE_TYPES = ["CCX", "CNOT", "CY", "CZ", "CRX", "CRY", "CU1", "CRZ", "U1", "U2", "U3", "H", "X", "Y", "Z", "S", "SDG", "T",
               "TDG", "RX", "RY", "RZ"]
 # microbench case -> gate types priced by it
-CASE_TYPES = {"h_x64_4q": ["H"], "rx_x64_4q": ["RX"], "u3_x64_4q": ["U3", "U2"], "t_x64_4q": ["T", "TDG", "S", "SDG", "U1"],
-              "rz_x64_4q": ["RZ"], "x_x64_4q": ["X", "Y"], "cz_x64_4q": ["CZ", "Z"], "cnot_x64_4q": ["CNOT", "CY", "CCX"]}
+CASE_TYPES = {"h_x64_4q": ["H"], "rx_x64_4q": ["RX"], "u3_x64_4q": ["U3", "U2"], "t_x64_4q": ["T", "TDG", "S", "SDG", "U1", "Z"],
+              "rz_x64_4q": ["RZ"], "x_x64_4q": ["X", "Y"], "cu1fan_x64_4q": ["CZ", "CU1"], "cnot_x64_4q": ["CNOT", "CY", "CCX"]}
 
 
 def main():
@@ -31,12 +31,14 @@ def main():
     print(f"hbm_gbs {32.0 * 2**30 / (sweep * 1e-3) / 1e9:.1f}")
     print(f"group_base_ms30 {max(base, 0.0):.3f}")
     for case, types in CASE_TYPES.items():
-        cost = (c[case]["ms_total"] * scale - base) / c[case]["gates"]
+        if case not in c:
+            continue
+        cost = max(0.02, (c[case]["ms_total"] * scale - base) / c[case]["gates"])
         for t in types:
             print(f"gate {GATE_TYPES.index(t)} {cost:.4f}")
     # controlled rotations: no dedicated case -> general-mask bodies cost about an uncontrolled rotation
     rx = (c["rx_x64_4q"]["ms_total"] * scale - base) / 64
-    for t in ("CRX", "CRY", "CRZ", "CU1", "RY"):
+    for t in ("CRX", "CRY", "CRZ", "RY"):
         print(f"gate {GATE_TYPES.index(t)} {rx * (0.75 if t != 'RY' else 0.8):.4f}")
     extra = (c["h_x96_12q"]["ms_total"] * scale - base - 96 * h_cost) / 2.0
     print(f"round_ms30 {max(extra, 0.0):.3f}")

@@ -180,6 +180,20 @@ def main():
         ls += cmul(re(i), im(i), "%0", "%1", "%2")
     print(asm_stmt(ls, ["fr", "fi", "nfi"], "cmul"))
     print("}")
+    print("__device__ __forceinline__ void hq_cmul_bit(double fr, double fi, int bit) {   // amplitudes whose register-index bit `bit` is 1")
+    print("    const double nfi = -fi;")
+    print("    switch (bit) {")
+    for b in range(RBITS):
+        ls = []
+        for i in range(R):
+            if i >> b & 1:
+                ls += cmul(re(i), im(i), "%0", "%1", "%2")
+        print(f"        case {b}:")
+        print(asm_stmt(ls, ["fr", "fi", "nfi"], "cmul", indent="            "))
+        print("            break;")
+    print("        default: break;")
+    print("    }")
+    print("}")
     print("__device__ __forceinline__ void hq_cmul_masked(double fr, double fi, uint32_t creg) {")
     print("    const double nfi = -fi;")
     for i in range(R):

@@ -33,6 +33,12 @@ def build(n, spec, count, qubits, seed=1):
         elif name in ("CZ", "CNOT", "CY"):
             q2 = qubits[(i + 1) % len(qubits)]
             c.add_gate(name, q, q2)
+        elif name in ("CU1F", "CZF"):     # fan: one operand on the hot qubits, the partner elsewhere (QFT ladders, CZ fans)
+            q2 = 12 + (i * 7) % (n - 12)
+            if name == "CZF":
+                c.add_gate("CZ", q, q2)
+            else:
+                c.add_gate("CU1", q, q2, params=(rng.uniform(0.1, 3.0),))
         elif name in ("CRX", "CRY", "CRZ", "CU1"):
             q2 = qubits[(i + 1) % len(qubits)]
             c.add_gate(name, q, q2, params=(rng.uniform(0.1, 3.0),))
@@ -76,6 +82,9 @@ def main():
         "x_x64_4q": (["X"], 64, hi4),
         "cz_x64_4q": (["CZ"], 64, hi4),
         "cnot_x64_4q": (["CNOT"], 64, hi4),
+        "cu1fan_x64_4q": (["CU1F"], 64, hi4),
+        "czfan_x64_4q": (["CZF"], 64, hi4),
+        "h_cu1fan_x64_4q": (["H", "CU1F", "CU1F", "CU1F", "CU1F", "CU1F", "CU1F", "CU1F"], 64, hi4),
         "mix5_x64_4q": (["H", "RX", "T", "RY", "CZ"], 64, hi4),
         "h_x64_1q": (["H"], 64, [9]),
         "h_x96_12q": (["H"], 96, list(range(12))),
