@@ -14,8 +14,10 @@
 //     __syncthreads() per gate, kernelOpt.cu:214-386).  Between rounds the tile is re-laid-out through
 //     shared memory (XOR-swizzled, conflict-free 128-bit accesses) to change the register qubits;
 //   * the lowered op list lives in shared memory; every (arithmetic class, target register bit, control
-//     register bit) combination is its own straight-line body selected by one jump, so a gate costs its
-//     FP64 instructions plus a handful of decode instructions;
+//     register bit) combination is its own straight-line body, all of them behind ONE brx.idx jump table, so a
+//     gate costs its FP64 instructions plus a handful of decode instructions;
+//   * gates of the form alpha*[[1,p],[q,-pq]] with p,q in {+-1} or {+-i} (H, RX/RY(+-pi/2)) are butterflies: two FP64
+//     adds per amplitude and no multiply; the alphas are collected into one scalar per launch;
 //   * diagonal gates that touch no register qubit of the round commute with everything else in it; they are
 //     folded, per thread, into ONE complex factor (a "diagonal run") applied with a single multiply pass;
 //   * controls and diagonal targets may sit on register bits, thread bits, or bits outside the tile
@@ -65,6 +67,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// volatile shared loads: issued exactly where written (the compiler otherwise sinks them behind the op-decode branches)
+__device__ __forceinline__ void lds_v4(uint32_t a, uint4& v) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+}
+__device__ __forceinline__ void lds_v2u64(uint32_t a, ulonglong2& v) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+}
+__device__ __forceinline__ void lds_v2f64(uint32_t a, double2& v) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- in-register gate arithmetic -----------------------------------------------------------------
@@ -80,13 +92,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #include "group_ops_gen_r3.inc"
 #endif
 namespace hq {
-
-// diag(d0,d1) on a thread/outside bit with register-bit controls (rare: e.g. CRZ with the control in registers)
-__device__ __forceinline__ void op_diag_t(const DevOp& o, uint64_t phys) {
-    const bool hi = (o.tphys == 0) || (phys & o.tphys);
-    if (!hi && (o.flags & 1u)) return;
-    hq_cmul_masked(hi ? o.m[6] : o.m[0], hi ? o.m[7] : o.m[1], o.creg);
-}
 
 // A run of diagonal gates none of which touches a register bit: every amplitude of the thread gets the same factor.
 // With creg != 0 the factor applies only to the amplitudes whose register-index bits creg are all 1: every diagonal gate
@@ -137,6 +142,10 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
     uint64_t* tbase_s = bar + 1;                                                       // base index of the landed tile
     DevRound* rounds_s = reinterpret_cast<DevRound*>(bar + 2);
     DevOp* ops_s = reinterpret_cast<DevOp*>(rounds_s + P.nrounds);
+    // per-round, per-thread index tables (the same for every tile): kept in shared memory so that a round starts after a
+    // shared-memory latency, not an L2 one (the tile write-back streams through L1 and evicts anything cached there)
+    uint64_t* gt_s = reinterpret_cast<uint64_t*>(ops_s + P.nops + 1);                  // +1: read-ahead slot
+    uint16_t* tb_s = reinterpret_cast<uint16_t*>(gt_s + (size_t)P.nrounds * NT);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -152,6 +161,11 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
         dst = reinterpret_cast<uint4*>(ops_s);
         const int m16 = P.nops * (int)(sizeof(DevOp) / 16);
         for (int i = tid; i < m16; i += NT) dst[i] = __ldg(src + i);
+        for (int r = 0; r < P.nrounds; ++r) {
+            gt_s[(size_t)r * NT + tid] = __ldg(P.gt + (size_t)r * NT + tid);
+            tb_s[(size_t)(2 * r) * NT + tid] = __ldg(P.tb + (size_t)(2 * r) * NT + tid);
+            tb_s[(size_t)(2 * r + 1) * NT + tid] = __ldg(P.tb + (size_t)(2 * r + 1) * NT + tid);
+        }
     }
     __syncthreads();
 
@@ -160,13 +174,14 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
 
     HQ_DECLARE_AMP_REGS();
     const uint32_t tile_s = smem_u32(tile);
+    const uint32_t ops_sa = smem_u32(ops_s);
     for (uint32_t it = 0; t < P.ntiles; t += gridDim.x, ++it) {
         mbar_wait(bar, it & 1);
         const uint64_t tbase = *tbase_s;
         for (int r = 0; r < P.nrounds; ++r) {
             const DevRound& rd = rounds_s[r];
-            const uint32_t tin = __ldg(P.tb + (size_t)(2 * r) * NT + tid);
-            const uint64_t phys = tbase | __ldg(P.gt + (size_t)r * NT + tid);
+            const uint32_t tin = tb_s[(size_t)(2 * r) * NT + tid];
+            const uint64_t phys = tbase | gt_s[(size_t)r * NT + tid];
             hq_load_amps(tile_s, tin, rd.ro_in);
 
             const bool last = rd.flags & 2u;
@@ -179,24 +194,50 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
                 if (tn < P.ntiles && tid < 32) issue_tile_load<K>(P, tn, tile, bar, tbase_s, tid);
             }
 
+            // Op headers (code, masks) are read one op AHEAD, while the current body runs; the eight coefficients are
+            // requested first thing in the iteration, so their latency hides behind the predicate checks and the jump.
             const int op_end = rd.op_end;
+            uint4 nhd;         // code, creg, flags, aux
+            ulonglong2 ncp;    // cphys, tphys
+            {
+                const uint32_t a = ops_sa + (uint32_t)rd.op_begin * (uint32_t)sizeof(DevOp);
+                lds_v4(a + 64, nhd);
+                lds_v2u64(a + 80, ncp);
+            }
             for (int op = rd.op_begin; op < op_end; ++op) {
-                const DevOp& o = ops_s[op];
-                const uint32_t code = o.code;
-                if (code == CODE_DIAG_RUN) {
-                    op_diag_run(&o + 1, (int)o.aux, phys, o.creg);
-                    op += (int)o.aux;
+                const uint4 hd = nhd;
+                const ulonglong2 cp = ncp;
+                const uint32_t pa = ops_sa + (uint32_t)op * (uint32_t)sizeof(DevOp);
+                double2 m01, m23, m45, m67;
+                lds_v2f64(pa, m01);
+                lds_v2f64(pa + 16, m23);
+                lds_v2f64(pa + 32, m45);
+                lds_v2f64(pa + 48, m67);
+                {   // next header (the slot after the last op is readable padding, never interpreted)
+                    const uint32_t skip = hd.x == CODE_DIAG_RUN ? hd.w : 0u;
+                    const uint32_t a = pa + (1u + skip) * (uint32_t)sizeof(DevOp);
+                    lds_v4(a + 64, nhd);
+                    lds_v2u64(a + 80, ncp);
+                }
+                if (hd.x == CODE_DIAG_RUN) {
+                    op_diag_run(ops_s + op + 1, (int)hd.w, phys, hd.y);
+                    op += (int)hd.w;
                     continue;
                 }
-                if ((phys & o.cphys) != o.cphys) continue;
-                if (code == CODE_DIAG_T) op_diag_t(o, phys);
-                else hq_apply_op(o);
+                if ((phys & cp.x) != cp.x) continue;
+                if (hd.x == CODE_DIAG_T) {
+                    const bool hi = (cp.y == 0) || (phys & cp.y);
+                    if (!hi && (hd.z & 1u)) continue;
+                    hq_cmul_masked(hi ? m67.x : m01.x, hi ? m67.y : m01.y, hd.y);
+                } else {
+                    hq_apply_op((hd.z >> 8) & 0xffu, hd.y, m01.x, m01.y, m23.x, m23.y, m45.x, m45.y, m67.x, m67.y);
+                }
             }
 
             if (last) {
                 hq_store_amps_global(P.state + phys, rd.go);
             } else {
-                const uint32_t tout = __ldg(P.tb + (size_t)(2 * r + 1) * NT + tid);
+                const uint32_t tout = tb_s[(size_t)(2 * r + 1) * NT + tid];
                 if (rd.flags & 1u) __syncthreads();
                 hq_store_amps(tile_s, tout, rd.ro_out);
                 __syncthreads();
@@ -211,11 +252,13 @@ struct HostGate {
     bool diag;
     double m[8];
     uint32_t kind;
+    double alpha[2];   // butterflies: the scalar taken out of the matrix (deferred to one factor per launch)
 };
 
 static inline uint32_t swz(uint32_t j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9) ^ (j >> 12)) & 7u); }
 
 static bool is_zero(double x) { return x == 0.0; }
+static bool rt_no_butterfly() { static const bool off = getenv("HQ_NO_BUTTERFLY") != nullptr; return off; }
 
 // Pick the arithmetic class from the matrix itself (the type tag is only a hint).
 static bool classify(const hq_gate& g, HostGate& h) {
@@ -234,6 +277,23 @@ static bool classify(const hq_gate& g, HostGate& h) {
         return !ident;   // identity gates are dropped
     }
     const bool imag0 = is_zero(m[1]) && is_zero(m[3]) && is_zero(m[5]) && is_zero(m[7]);
+    if (g.control < 0 && g.control2 < 0 && !rt_no_butterfly()) {
+        // alpha * [[1, p],[q, -p q]] with p, q both real units or both imaginary units?  (tolerance: cos(pi/4) and
+        // sin(pi/4) differ in the last bit; 1e-14 relative is far inside the 1e-10 amplitude budget)
+        typedef std::complex<double> C;
+        const C a(m[0], m[1]), b(m[2], m[3]), c(m[4], m[5]), d(m[6], m[7]);
+        if (std::abs(a) > 0.5) {
+            const C pp = b / a, qq = c / a, rr = d / a;
+            for (int v = 0; v < 8; ++v) {
+                const C pv(HQ_BF_PQ[v][0], HQ_BF_PQ[v][1]), qv(HQ_BF_PQ[v][2], HQ_BF_PQ[v][3]);
+                if (std::abs(pp - pv) < 1e-14 && std::abs(qq - qv) < 1e-14 && std::abs(rr + pv * qv) < 1e-14) {
+                    h.kind = OP_BF0 + v;
+                    h.alpha[0] = a.real(); h.alpha[1] = a.imag();
+                    return true;
+                }
+            }
+        }
+    }
     if (dia0 && m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0) h.kind = OP_SWAP;
     else if (dia0 && m[2] == 0.0 && m[3] == -1.0 && m[4] == 0.0 && m[5] == 1.0) h.kind = OP_YL;
     else if (imag0) h.kind = OP_REAL;
@@ -348,6 +408,11 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         }
     }
     const int nrounds = (int)rounds.size();
+    // butterflies leave their scalars behind: one factor for the whole launch, applied with the last round's diagonal run
+    std::complex<double> launch_scale(1.0, 0.0);
+    bool any_bfly = false;
+    for (const HostGate& h : hg)
+        if (h.kind >= OP_BF0 && h.kind <= OP_BF7 && !h.diag) { launch_scale *= std::complex<double>(h.alpha[0], h.alpha[1]); any_bfly = true; }
     const bool trace_plan = getenv("HQ_TRACE_PLAN") != nullptr;
 
     // ---- encode ----
@@ -406,7 +471,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                 if (in_reg(tgt)) {
                     const uint32_t tbit = reg_of_tile[phys_to_tile[tgt]];
                     const bool zflip = d0one && h.m[6] == -1.0 && h.m[7] == 0.0;
-                    o.code = op_code(zflip ? OP_ZFLIP : OP_DIAG_R, tbit, cbc);
+                    o.code = op_code(zflip ? OP_ZFLIP : (d0one ? OP_DIAG_R1 : OP_DIAG_R), tbit, cbc);
                     if (d0one && o.creg == 0) {
                         // diag(1,d) whose ONLY register operand is tbit (T on a register qubit, the cu1 ladder of a QFT,
                         // CZ fans): "multiply by d where tbit = 1 and the other operands are 1".  Consecutive ones on the
@@ -435,6 +500,10 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                 const uint32_t cb = (generic_only && cbc != 0) ? CBC_GENERIC : cbc;
                 if (h.kind == OP_SWAP || h.kind == OP_YL) {
                     o.code = op_code(h.kind, tbit, cb);
+                    body.push_back(o);
+                } else if (h.kind >= OP_BF0 && h.kind <= OP_BF7) {
+                    std::memset(o.m, 0, sizeof(o.m));
+                    o.code = op_code(h.kind, tbit, 0);
                     body.push_back(o);
                 } else {
                     // in-place LU form needs a diagonal entry d that is not small; otherwise apply X*M first and
@@ -499,6 +568,13 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             gt[(size_t)r * NT + t] = pdep64(j, tile_mask);
         }
         flush(~0u);
+        if (is_last && any_bfly) {   // scalar entry (tphys = 0: always d1, no predicate) of the round's diagonal run
+            DevOp sc{};
+            sc.code = CODE_DIAG_T;
+            sc.m[0] = sc.m[6] = launch_scale.real();
+            sc.m[1] = sc.m[7] = launch_scale.imag();
+            run.push_back(sc);
+        }
         for (DevOp& o : body)   // body index for the kernel's single indexed branch
             if (o.code < CODE_DIAG_T) o.flags |= (uint32_t)HQ_OP_BODY_INDEX[o.code] << 8;
         d.op_begin = (int)dops.size();
@@ -549,7 +625,8 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         }
         p.nseg = nseg;
     }
-    plan->smem = (size_t)(16u << K) + 16 + (size_t)nrounds * sizeof(DevRound) + dops.size() * sizeof(DevOp);
+    plan->smem = (size_t)(16u << K) + 16 + (size_t)nrounds * sizeof(DevRound) + (dops.size() + 1) * sizeof(DevOp)   // +1: read-ahead slot
+                 + (size_t)nrounds * NT * (8 + 4);                                                                 // gt, tb tables
     if (plan->smem > 227 * 1024) {
         delete plan;
         set_error("gate group does not fit in shared memory (too many gates/rounds for one launch): split it");

@@ -18,16 +18,24 @@ constexpr int MIN_RUN_BITS = 3;   // tiles are made of >= 128-byte contiguous ru
 // Arithmetic classes.  Classes < OPK_TEMPLATED are instantiated per (target register bit, control case).
 enum OpKind : uint32_t {
     OP_GEN = 0,     // general complex 2x2 on a register bit
-    OP_REAL,        // real 2x2 (H, RY, ...)
+    OP_REAL,        // real 2x2 (RY, ...)
     OP_RXL,         // [[a, i b],[i c, d]] with real a,b,c,d (RX, ...)
     OP_SWAP,        // X / CNOT / CCX
     OP_YL,          // [[0, -i],[i, 0]]
     OP_DIAG_R,      // diag(d0, d1), target is a register bit
     OP_ZFLIP,       // diag(1, -1) on a register bit: sign flips only (Z / CZ)
+    OP_DIAG_R1,     // diag(1, d1) on a register bit: only the "hi" half is multiplied
+    // Butterflies: uncontrolled M = alpha * [[1, p],[q, -p q]] with p, q both in {+1,-1} or both in {+i,-i} (H, RX(+-pi/2),
+    // RY(+-pi/2), ...): two FP64 adds per amplitude, no multiplies; alpha is deferred to ONE scalar factor per launch.
+    OP_BF0,         // variant v = OP_BFv - OP_BF0 indexes HQ_BF_PQ below
+    OP_BF7 = OP_BF0 + 7,
     OPK_TEMPLATED,
     OP_DIAG_T = OPK_TEMPLATED,   // diag(d0, d1) whose target is a thread/outside bit, with register-bit controls
     OP_DIAG_RUN,                 // header of `aux` following entries: diagonal gates that touch no register bit
 };
+// (p, q) of butterfly variant v as {re p, im p, re q, im q}
+constexpr double HQ_BF_PQ[8][4] = {{1, 0, 1, 0},  {1, 0, -1, 0},  {-1, 0, 1, 0},  {-1, 0, -1, 0},
+                                   {0, 1, 0, 1},  {0, 1, 0, -1},  {0, -1, 0, 1},  {0, -1, 0, -1}};
 // control case of a templated op: 0 = no register-bit control, 1..4 = exactly register bit (cbc-1), 5 = generic mask
 constexpr uint32_t CBC_GENERIC = 5;
 #define HQ_OP_CODE(kind, tb, cbc) ((uint32_t)(kind) * 24u + (uint32_t)(tb) * 6u + (uint32_t)(cbc))
@@ -39,7 +47,7 @@ struct alignas(16) DevOp {
     double m[8];       // row-major 2x2 (re, im); diagonal ops use m[0..1] = d0, m[6..7] = d1
     uint32_t code;     // op_code(kind, tbit, cbc) / CODE_DIAG_T / CODE_DIAG_RUN
     uint32_t creg;     // all register-index control bits
-    uint32_t flags;    // bit0: d0 == 1 (the "lo" half of a diagonal is untouched)
+    uint32_t flags;    // bit0: d0 == 1 (the "lo" half of a diagonal is untouched); bits 8..15: body index of hq_apply_op
     uint32_t aux;      // CODE_DIAG_RUN: number of entries that follow
     uint64_t cphys;    // controls outside the registers, as a mask over the physical local index
     uint64_t tphys;    // diagonal ops with a non-register target: its physical bit (0 = scalar, always d1)

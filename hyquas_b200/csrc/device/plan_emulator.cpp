@@ -84,11 +84,21 @@ int applyOp(Amp* a, const DevOp* op, uint64_t phys) {
             case OP_SWAP: a[lo] = y; a[hi] = x; break;
             case OP_YL: a[lo] = {y.y, -y.x}; a[hi] = {-x.y, x.x}; break;
             case OP_DIAG_R:
-                if (!(o.flags & 1u)) cmul(a[lo], m[0], m[1]);
+                cmul(a[lo], m[0], m[1]);
                 cmul(a[hi], m[6], m[7]);
                 break;
+            case OP_DIAG_R1: cmul(a[hi], m[6], m[7]); break;
             case OP_ZFLIP: a[hi] = {-y.x, -y.y}; break;
-            default: std::fprintf(stderr, "plan emulator: bad op code %u\n", o.code); std::abort();
+            default: {
+                if (kind >= OP_BF0 && kind <= OP_BF7) {   // [[1, p],[q, -p q]] by definition (the PTX uses add/sub butterflies)
+                    const double* pq = HQ_BF_PQ[kind - OP_BF0];
+                    const std::complex<double> pp(pq[0], pq[1]), qq(pq[2], pq[3]), lo_(x.x, x.y), hi_(y.x, y.y);
+                    const std::complex<double> nl = lo_ + pp * hi_, nh = qq * lo_ - pp * qq * hi_;
+                    a[lo] = {nl.real(), nl.imag()}; a[hi] = {nh.real(), nh.imag()};
+                    break;
+                }
+                std::fprintf(stderr, "plan emulator: bad op code %u\n", o.code); std::abort();
+            }
         }
     }
     return 0;

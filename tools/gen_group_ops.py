@@ -1,23 +1,37 @@
 #!/usr/bin/env python
-"""Generates hyquas_b200/csrc/device/group_ops_gen.inc: the in-register gate arithmetic of the gate-group kernel.
+"""Generates hyquas_b200/csrc/device/group_ops_gen_r{3,4}.inc: the in-register gate arithmetic of the gate-group kernel.
 
 Why generated inline PTX: the 16 amplitudes a thread holds (32 FP64 values) must stay in the SAME registers across the
-op loop and its 100+ way switch.  Written as a C++ array, LLVM turns them into 64 SSA webs with phi nodes at every
+op loop and its 100+ way dispatch.  Written as a C++ array, LLVM turns them into 64 SSA webs with phi nodes at every
 join and ptxas ends up copying the whole set once per gate (measured: 65 % of all executed instructions were MOVs).
 Here the amplitudes live in named PTX registers (hqa0..hqa31) that the C++ compiler never sees; every op body
 updates them in place, so a gate costs its FP64 instructions and nothing else.
 
+All op bodies live in ONE asm statement behind a single `brx.idx` jump table (a C++ switch over the same bodies compiled
+to a 7-deep tree of compare+branch per gate).  Operands of that statement are fixed:
+    %0 = body index, %1 = register-index control mask (creg), %2..%9 = the op's eight coefficients m[0..7].
+
     python tools/gen_group_ops.py 4 > hyquas_b200/csrc/device/group_ops_gen_r4.inc     (argument = register qubits per thread)
 
 Register naming: amplitude i (0..15) = (hqa{2i}, hqa{2i+1}) = (re, im).
-Op numbering must match group_plan.h: code = kind*24 + tb*6 + cbc, cbc: 0 none, 1..4 register bit cbc-1, 5 generic.
+Op numbering must match group_plan.h: code = kind*24 + tb*6 + cbc, cbc: 0 none, 1..4 register bit cbc-1, 5 generic mask.
+
+tests/test_group_ops_ptx.py interprets the generated PTX of every body on random data and checks it against the 2x2
+matrix the planner means by it, so the arithmetic is proven on a machine without a GPU.
 """
 import sys
 
-RBITS = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-R = 1 << RBITS
-KINDS = ["GEN", "REAL", "RXL", "SWAP", "YL", "DIAG_R", "ZFLIP"]
+# must match enum OpKind in group_plan.h
+KINDS = ["GEN", "REAL", "RXL", "SWAP", "YL", "DIAG_R", "ZFLIP", "DIAG_R1",
+         "BF0", "BF1", "BF2", "BF3", "BF4", "BF5", "BF6", "BF7"]
 GENERIC_ONLY = {"GEN", "REAL", "RXL", "YL"}   # single-control cases are routed to the generic mask on the host
+NO_CONTROL = {k for k in KINDS if k.startswith("BF")}   # butterflies defer their scale: uncontrolled only
+# butterfly variants: M = alpha * [[1, p], [q, -p*q]], (p, q) both real or both imaginary units
+BF_PQ = [(1, 1), (1, -1), (-1, 1), (-1, -1), (1j, 1j), (1j, -1j), (-1j, 1j), (-1j, -1j)]
+M = {f"m{i}": f"%{i + 2}" for i in range(8)}
+CREG = "%1"
+NEG = "0x8000000000000000"
+TWO = "0d4000000000000000"
 
 
 def re(i):
@@ -28,7 +42,7 @@ def im(i):
     return f"hqa{2 * i + 1}"
 
 
-def pairs(tb):
+def pairs(tb, R):
     out = []
     for p in range(R // 2):
         lo = ((p >> tb) << (tb + 1)) | (p & ((1 << tb) - 1))
@@ -55,109 +69,116 @@ def cmul(zx, zy, pr, pi, npi, t="hqt"):
             f"fma.rn.f64 {zy}, {pi}, {zx}, {zy};", f"mov.f64 {zx}, {t};"]
 
 
-NEG = "0x8000000000000000"
+def bfly(u, v, sigma, tau):
+    """u' = u + sigma*v ; v' = tau*(u - sigma*v), two FP64 instructions, in place (u' = 2u - tau*v')."""
+    if tau > 0:
+        first = [f"sub.f64 {v}, {u}, {v};"] if sigma > 0 else [f"add.f64 {v}, {u}, {v};"]
+        return first + [f"neg.f64 hqt, {v};", f"fma.rn.f64 {u}, {u}, {TWO}, hqt;"]
+    first = [f"sub.f64 {v}, {v}, {u};"] if sigma > 0 else [f"neg.f64 hqt, {u};", f"sub.f64 {v}, hqt, {v};"]
+    return first + [f"fma.rn.f64 {u}, {u}, {TWO}, {v};"]
+
+
+def bfly_pairs(p, q, lo, hi):
+    """Scalar butterflies of M = [[1,p],[q,-pq]] on amplitudes lo=(a,b), hi=(c,d): list of (u, v, sigma, tau).
+
+    lo' = lo + w, hi' = q*(lo - w) with w = p*hi.  For real p the scalar pairs are (a,c),(b,d); for imaginary p they are
+    (a,d),(b,c), and an imaginary q puts q*(lo - w) back into the natural registers with a sign."""
+    a, b, c, d = re(lo), im(lo), re(hi), im(hi)
+    if p.imag == 0:
+        s = 1 if p.real > 0 else -1            # w = (s c, s d)
+        t = 1 if q.real > 0 else -1            # hi' = t * (a - s c, b - s d)
+        assert q.imag == 0
+        return [(a, c, s, t), (b, d, s, t)]
+    s = 1 if p.imag > 0 else -1                # w = s*i*(c + i d) = (-s d, s c)
+    t = 1 if q.imag > 0 else -1                # hi' = t*i*(x + i y) = (-t y, t x) with x = a + s d (lands in d), y = b - s c (in c)
+    assert q.real == 0
+    # register d: u = a, v = d: u' = a - s d ... careful: lo'.re = a + w.re = a - s d ; x = a - w.re = a + s d
+    # so for (a, d): sigma = -s, and d' = hi'.im = t * x = t * (a + s d) = tau*(u - sigma v) with tau = t
+    # for (b, c): lo'.im = b + w.im = b + s c -> sigma = s ; y = b - s c ; c' = hi'.re = -t * y -> tau = -t
+    return [(a, d, -s, t), (b, c, s, -t)]
 
 
 def pair_body(kind, lo, hi):
-    """PTX for one (lo, hi) pair.  Returns (lines, operand names in order, needs_temp)."""
+    """PTX lines for one (lo, hi) pair; coefficients are the statement operands m0..m7 (and negations hqn*)."""
     if kind == "REAL":      # m = {c, d, e, f}
-        ops = ["c", "d", "e", "f"]
-        ls = lu2(re(lo), re(hi), "%0", "%1", "%2", "%3") + lu2(im(lo), im(hi), "%0", "%1", "%2", "%3")
-        return ls, ops
-    if kind == "RXL":       # (lo.x, hi.y) with {c,d,e,f}; (lo.y, hi.x) with {-c,d,e,-f}  -> operands c,d,e,f,nc,nf
-        ops = ["c", "d", "e", "f", "nc", "nf"]
-        ls = lu2(re(lo), im(hi), "%0", "%1", "%2", "%3") + lu2(im(lo), re(hi), "%4", "%1", "%2", "%5")
-        return ls, ops
-    if kind == "GEN":       # hi <- c*lo + d*hi ; lo <- e*lo + f*hi
-        ops = ["cr", "ci", "dr", "di", "er", "ei", "fr", "fi", "nci", "ndi", "nei", "nfi"]
-        ls = caxpby(re(hi), im(hi), re(lo), im(lo), "%2", "%3", "%9", "%0", "%1", "%8")
-        ls += caxpby(re(lo), im(lo), re(hi), im(hi), "%4", "%5", "%10", "%6", "%7", "%11")
-        return ls, ops
+        return lu2(re(lo), re(hi), M["m0"], M["m1"], M["m2"], M["m3"]) + lu2(im(lo), im(hi), M["m0"], M["m1"], M["m2"], M["m3"])
+    if kind == "RXL":       # (lo.x, hi.y) with {c,d,e,f}; (lo.y, hi.x) with {-c,d,e,-f}
+        return lu2(re(lo), im(hi), M["m0"], M["m1"], M["m2"], M["m3"]) + lu2(im(lo), re(hi), "hqn0", M["m1"], M["m2"], "hqn3")
+    if kind == "GEN":       # m = {c, d, e, f} complex: hi <- c*lo + d*hi ; lo <- e*lo + f*hi
+        ls = caxpby(re(hi), im(hi), re(lo), im(lo), M["m2"], M["m3"], "hqn3", M["m0"], M["m1"], "hqn1")
+        ls += caxpby(re(lo), im(lo), re(hi), im(hi), M["m4"], M["m5"], "hqn5", M["m6"], M["m7"], "hqn7")
+        return ls
     if kind == "SWAP":
         ls = []
         for x, y in ((re(lo), re(hi)), (im(lo), im(hi))):
             ls += [f"mov.f64 hqt, {x};", f"mov.f64 {x}, {y};", f"mov.f64 {y}, hqt;"]
-        return ls, []
+        return ls
     if kind == "YL":        # lo' = -i*hi = (hi.y, -hi.x) ; hi' = i*lo = (-lo.y, lo.x)
-        ls = [f"mov.f64 hqt, {re(lo)};", f"mov.f64 hqu, {im(lo)};",
-              f"mov.f64 {re(lo)}, {im(hi)};", f"xor.b64 {im(lo)}, {re(hi)}, {NEG};",
-              f"xor.b64 {re(hi)}, hqu, {NEG};", f"mov.f64 {im(hi)}, hqt;"]
-        return ls, []
-    if kind == "DIAG_R1":   # hi *= d1
-        return cmul(re(hi), im(hi), "%0", "%1", "%2"), ["r1", "i1", "ni1"]
-    if kind == "DIAG_R01":  # lo *= d0, hi *= d1
-        return (cmul(re(lo), im(lo), "%3", "%4", "%5") + cmul(re(hi), im(hi), "%0", "%1", "%2"),
-                ["r1", "i1", "ni1", "r0", "i0", "ni0"])
+        return [f"mov.f64 hqt, {re(lo)};", f"mov.f64 hqu, {im(lo)};",
+                f"mov.f64 {re(lo)}, {im(hi)};", f"xor.b64 {im(lo)}, {re(hi)}, {NEG};",
+                f"xor.b64 {re(hi)}, hqu, {NEG};", f"mov.f64 {im(hi)}, hqt;"]
+    if kind == "DIAG_R1":   # hi *= d1 = (m6, m7)
+        return cmul(re(hi), im(hi), M["m6"], M["m7"], "hqn7")
+    if kind == "DIAG_R":    # lo *= d0 = (m0, m1), hi *= d1
+        return cmul(re(lo), im(lo), M["m0"], M["m1"], "hqn1") + cmul(re(hi), im(hi), M["m6"], M["m7"], "hqn7")
     if kind == "ZFLIP":
-        return [f"xor.b64 {re(hi)}, {re(hi)}, {NEG};", f"xor.b64 {im(hi)}, {im(hi)}, {NEG};"], []
+        return [f"xor.b64 {re(hi)}, {re(hi)}, {NEG};", f"xor.b64 {im(hi)}, {im(hi)}, {NEG};"]
+    if kind.startswith("BF"):
+        p, q = BF_PQ[int(kind[2:])]
+        ls = []
+        for u, v, s, t in bfly_pairs(complex(p), complex(q), lo, hi):
+            ls += bfly(u, v, s, t)
+        return ls
     raise ValueError(kind)
 
 
-OPERAND_EXPR = {
-    "REAL": {"c": "o.m[0]", "d": "o.m[1]", "e": "o.m[2]", "f": "o.m[3]"},
-    "RXL": {"c": "o.m[0]", "d": "o.m[1]", "e": "o.m[2]", "f": "o.m[3]", "nc": "-o.m[0]", "nf": "-o.m[3]"},
-    "GEN": {"cr": "o.m[0]", "ci": "o.m[1]", "dr": "o.m[2]", "di": "o.m[3]", "er": "o.m[4]", "ei": "o.m[5]",
-            "fr": "o.m[6]", "fi": "o.m[7]", "nci": "-o.m[1]", "ndi": "-o.m[3]", "nei": "-o.m[5]", "nfi": "-o.m[7]"},
-    "DIAG_R1": {"r1": "o.m[6]", "i1": "o.m[7]", "ni1": "-o.m[7]"},
-    "DIAG_R01": {"r1": "o.m[6]", "i1": "o.m[7]", "ni1": "-o.m[7]", "r0": "o.m[0]", "i0": "o.m[1]", "ni0": "-o.m[1]"},
-}
+NEGS_NEEDED = {"RXL": [0, 3], "GEN": [1, 3, 5, 7], "DIAG_R1": [7], "DIAG_R": [1, 7]}
 
 
-def asm_stmt(lines, operands, kind, indent="    "):
-    body = " ".join(lines)
-    text = '"{ .reg .f64 hqt, hqu; ' + body + ' }"'
-    if operands:
-        ins = ", ".join(f'"d"({name})' for name in operands)
-        return f"{indent}asm volatile({text} :: {ins});"
-    return f"{indent}asm volatile({text});"
-
-
-def emit_body(kind, tb, cbc):
-    """C++ statements applying `kind` on target register bit tb with control case cbc."""
-    out = []
-    variants = [kind]
-    if kind == "DIAG_R":
-        variants = ["DIAG_R1", "DIAG_R01"]
-    for vi, var in enumerate(variants):
-        decl = OPERAND_EXPR.get(var, {})
-        names = None
-        stmts = []
-        sel = []
-        for lo, hi in pairs(tb):
-            if 1 <= cbc <= RBITS and not (lo >> (cbc - 1)) & 1:
-                continue
-            ls, names = pair_body(var, lo, hi)
-            sel.append((lo, ls))
-        pre = [f"    const double {n} = {decl[n]};" for n in (names or [])]
-        if cbc == 5:
-            for lo, ls in sel:
-                stmts.append(f"    if (({lo}u & creg) == creg) {{")
-                stmts.append(asm_stmt(ls, names, var, indent="        "))
-                stmts.append("    }")
+def body_lines(kind, tb, cbc, rbits):
+    """Straight-line PTX of one dispatch target: `kind` on target register bit tb with control case cbc."""
+    R = 1 << rbits
+    out = [f"neg.f64 hqn{i}, {M[f'm{i}']};" for i in NEGS_NEEDED.get(kind, [])]
+    for lo, hi in pairs(tb, R):
+        if 1 <= cbc <= 4 and not (lo >> (cbc - 1)) & 1:
+            continue
+        ls = pair_body(kind, lo, hi)
+        if cbc == 5:   # generic register-control mask: pair participates iff (lo & creg) == creg
+            out += [f"and.b32 hqx, {CREG}, {(~lo) & (R - 1)};", "setp.eq.u32 hqp, hqx, 0;"]
+            out += ["@hqp " + l for l in ls]
         else:
-            # a few pairs per asm statement keeps the strings readable and lets ptxas interleave freely
-            flat = []
-            for _, ls in sel:
-                flat += ls
-            stmts.append(asm_stmt(flat, names, var))
-        block = pre + stmts
-        if kind == "DIAG_R":
-            cond = "if (o.flags & 1u) {" if vi == 0 else "} else {"
-            out.append("    " + cond)
-            out += ["    " + b for b in block]
-            if vi == 1:
-                out.append("    }")
-        else:
-            out += block
+            out += ls
     return out
 
 
+def catalog(rbits):
+    """[(code, kind, tb, cbc, lines)] in body-index order."""
+    out = []
+    for k, kind in enumerate(KINDS):
+        for tb in range(rbits):
+            for cbc in range(6):
+                if 1 <= cbc <= 4 and (cbc - 1 == tb or cbc > rbits or kind in GENERIC_ONLY):
+                    continue
+                if cbc != 0 and kind in NO_CONTROL:
+                    continue
+                out.append((k * 24 + tb * 6 + cbc, kind, tb, cbc, body_lines(kind, tb, cbc, rbits)))
+    return out
+
+
+def asm_stmt(lines, operands, indent="    "):
+    body = " ".join(lines)
+    text = '"{ .reg .f64 hqt; ' + body + ' }"'
+    ins = ", ".join(f'"d"({name})' for name in operands)
+    return f"{indent}asm volatile({text} :: {ins});"
+
+
 def main():
+    rbits = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    R = 1 << rbits
     print("// GENERATED by tools/gen_group_ops.py -- do not edit.  See that script for the why and the register naming.")
     print("// clang-format off")
     print(f'#define HQ_DECLARE_AMP_REGS() asm volatile(".reg .f64 hqa<{2 * R}>;")')
     print()
-    # loads / stores
     print("// tile (shared memory, 32-bit shared address of amplitude index 0) <-> amplitude registers")
     print("__device__ __forceinline__ void hq_load_amps(uint32_t tile_s, uint32_t tin, const uint16_t* ro) {")
     for i in range(R):
@@ -172,24 +193,27 @@ def main():
         print(f'    asm volatile("st.global.v2.f64 [%0], {{{re(i)}, {im(i)}}};" :: "l"(base + go[{i}]) : "memory");')
     print("}")
     print()
-    # complex multiply of all / masked amplitudes by a runtime factor
+
+    def cm(z, fr="%0", fi="%1", nfi="%2"):
+        return cmul(re(z), im(z), fr, fi, nfi)
+
     print("__device__ __forceinline__ void hq_cmul_all(double fr, double fi) {")
     print("    const double nfi = -fi;")
     ls = []
     for i in range(R):
-        ls += cmul(re(i), im(i), "%0", "%1", "%2")
-    print(asm_stmt(ls, ["fr", "fi", "nfi"], "cmul"))
+        ls += cm(i)
+    print(asm_stmt(ls, ["fr", "fi", "nfi"]))
     print("}")
     print("__device__ __forceinline__ void hq_cmul_bit(double fr, double fi, int bit) {   // amplitudes whose register-index bit `bit` is 1")
     print("    const double nfi = -fi;")
     print("    switch (bit) {")
-    for b in range(RBITS):
+    for b in range(rbits):
         ls = []
         for i in range(R):
             if i >> b & 1:
-                ls += cmul(re(i), im(i), "%0", "%1", "%2")
+                ls += cm(i)
         print(f"        case {b}:")
-        print(asm_stmt(ls, ["fr", "fi", "nfi"], "cmul", indent="            "))
+        print(asm_stmt(ls, ["fr", "fi", "nfi"], indent="            "))
         print("            break;")
     print("        default: break;")
     print("    }")
@@ -198,38 +222,35 @@ def main():
     print("    const double nfi = -fi;")
     for i in range(R):
         print(f"    if (({i}u & creg) == creg) {{")
-        print(asm_stmt(cmul(re(i), im(i), "%0", "%1", "%2"), ["fr", "fi", "nfi"], "cmul", indent="        "))
+        print(asm_stmt(cm(i), ["fr", "fi", "nfi"], indent="        "))
         print("    }")
     print("}")
     print()
-    cases = []
-    for k, kind in enumerate(KINDS):
-        for tb in range(RBITS):
-            for cbc in range(6):
-                if 1 <= cbc <= 4 and (cbc - 1 == tb or cbc > RBITS or kind in GENERIC_ONLY):
-                    continue
-                code = k * 24 + tb * 6 + cbc
-                print(f"__device__ __forceinline__ void hq_op_{code}(const hq::DevOp& o) {{   // {kind} tb={tb} cbc={cbc}")
-                if cbc == 5:
-                    print("    const uint32_t creg = o.creg;")
-                for l in emit_body(kind, tb, cbc):
-                    print(l)
-                print("}")
-                cases.append(code)
-    print()
-    # dense body index: a contiguous 0..N-1 switch compiles to ONE indexed branch (the sparse switch on `code` became a
-    # tree of compares + small BRX tables, ~8 dependent branches per gate).  The planner stores the index in flags[15:8].
-    print(f"#define HQ_OP_BODIES {len(cases)}")
-    table = [255] * (max(cases) + 1)
-    for i, c in enumerate(cases):
-        table[c] = i
+
+    cat = catalog(rbits)
+    print(f"#define HQ_OP_BODIES {len(cat)}")
+    table = [255] * (len(KINDS) * 24)
+    for i, (code, *_rest) in enumerate(cat):
+        table[code] = i
+    assert len(cat) < 255
     print("static const unsigned char HQ_OP_BODY_INDEX[] = {" + ", ".join(str(v) for v in table) + "};")
-    print("__device__ __forceinline__ void hq_apply_op(const hq::DevOp& o) {")
-    print("    switch ((o.flags >> 8) & 0xffu) {")
-    for i, c in enumerate(cases):
-        print(f"        case {i}: hq_op_{c}(o); break;")
-    print("        default: break;")
-    print("    }")
+    print("// one jump, one body: `body` is HQ_OP_BODY_INDEX[code], warp-uniform")
+    print("__device__ __forceinline__ void hq_apply_op(uint32_t body, uint32_t creg, double m0, double m1, double m2, double m3,")
+    print("                                            double m4, double m5, double m6, double m7) {")
+    print("    asm volatile(\"{\\n\"")
+    print('        ".reg .f64 hqt, hqu, hqn0, hqn1, hqn3, hqn5, hqn7;\\n"')
+    print('        ".reg .pred hqp;\\n"')
+    print('        ".reg .b32 hqx;\\n"')
+    labels = ", ".join(f"HQB{i}" for i in range(len(cat)))
+    print(f'        "HQTS: .branchtargets {labels};\\n"')
+    print('        "brx.idx.uni %0, HQTS;\\n"')
+    for i, (code, kind, tb, cbc, lines) in enumerate(cat):
+        print(f'        "HQB{i}:\\n"   // {kind} tb={tb} cbc={cbc} (code {code})')
+        for l in lines:
+            print(f'        "{l}\\n"')
+        print('        "bra.uni HQEND;\\n"')
+    print('        "HQEND:\\n"')
+    print('        "}" :: "r"(body), "r"(creg), "d"(m0), "d"(m1), "d"(m2), "d"(m3), "d"(m4), "d"(m5), "d"(m6), "d"(m7));')
     print("}")
     print("// clang-format on")
 

@@ -9,6 +9,7 @@ Used (a) to calibrate the evaluator (tools/calibrate.py reads the JSON) and (b) 
 import argparse
 import ctypes
 import json
+import math
 import os
 import random
 import sys
@@ -26,6 +27,8 @@ def build(n, spec, count, qubits, seed=1):
         q = qubits[i % len(qubits)]
         if name in ("H", "X", "Y", "Z", "S", "T", "SDG", "TDG"):
             c.add_gate(name, q)
+        elif name in ("RXH", "RYH"):       # the supremacy circuits' rx(pi/2), ry(pi/2): butterfly class
+            c.add_gate(name[:2], q, params=(math.pi / 2,))
         elif name in ("RX", "RY", "RZ", "U1"):
             c.add_gate(name, q, params=(rng.uniform(0.1, 3.0),))
         elif name == "U3":
@@ -51,25 +54,28 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="comma-separated tile-kernel case names; skips the FP64/copy/dense sections")
     args = ap.parse_args()
+    only = [x for x in args.only.split(",") if x]
     n = args.qubits
     api.init()
     res = {"qubits": n, "lib_suffix": os.environ.get("HQ_LIB_SUFFIX", ""), "cases": {}}
     v = ctypes.c_double()
-    for kind, key in ((0, "fp64_fma_tflops"), (1, "fp64_mma_tflops")):
+    for kind, key in [] if only else ((0, "fp64_fma_tflops"), (1, "fp64_mma_tflops")):
         check(lib.hq_microbench_fp64(kind, v))
         res[key] = v.value
     res["dmma_tflops_by_warps_per_sm"] = {}
-    for w in (4, 8, 12, 16, 24, 32):
+    for w in () if only else (4, 8, 12, 16, 24, 32):
         check(lib.hq_microbench_fp64(10 + w, v))
         res["dmma_tflops_by_warps_per_sm"][w] = v.value
-    print("dmma by warps/SM:", {k: round(x, 1) for k, x in res["dmma_tflops_by_warps_per_sm"].items()}, flush=True)
+    if not only:
+        print("dmma by warps/SM:", {k: round(x, 1) for k, x in res["dmma_tflops_by_warps_per_sm"].items()}, flush=True)
     st = ctypes.c_void_p()
     check(lib.hq_state_alloc(n, ctypes.byref(st)))
     check(lib.hq_microbench_copy(st, n, v))
     res["copy_gbs"] = v.value
     check(lib.hq_state_free(st))
-    print(json.dumps({k: res[k] for k in ("fp64_fma_tflops", "fp64_mma_tflops", "copy_gbs")}), flush=True)
+    print(json.dumps({k: res.get(k) for k in ("fp64_fma_tflops", "fp64_mma_tflops", "copy_gbs")}), flush=True)
 
     hi4 = [8, 9, 10, 11]
     cases = {
@@ -94,7 +100,16 @@ def main():
         "h_x256_4q": (["H"], 256, hi4),
     }
     os.environ["HQ_BACKEND"] = "group"      # these cases price the TILE kernel; the hybrid partitioner would fuse them
+    cases.update({
+        "h_x96_12q_hi": (["H"], 96, list(range(16, 28))),     # same, on qubits the partitioner is free to place
+        "t_x96_12q": (["T"], 96, list(range(12))),
+        "sup5_x64_4q": (["H", "RXH", "T", "RYH", "CZ"], 64, hi4),
+        "sup5_x96_12q": (["H", "RXH", "T", "RYH", "CZ"], 96, list(range(12))),
+        "mix5_x256_12q": (["H", "RX", "T", "RY", "CZ"], 256, list(range(12))),
+    })
     for name, (spec, count, qubits) in cases.items():
+        if only and name not in only:
+            continue
         c = build(n, spec, count, qubits)
         c.compile()
         c.prepare_state()
@@ -108,6 +123,10 @@ def main():
               flush=True)
         c.close()
     os.environ.pop("HQ_BACKEND", None)
+    if only:
+        if args.out:
+            json.dump(res, open(args.out, "w"), indent=1)
+        return
     # fused dense kernel: one or several random unitaries on m qubits, 2^n amplitudes
     import numpy as np
     rng = np.random.default_rng(5)
