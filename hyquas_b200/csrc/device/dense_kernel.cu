@@ -462,19 +462,25 @@ extern "C" int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int 
     HQ_REQUIRE(plan && state, "null plan or state");
     HQ_REQUIRE(rt().ready && plan->dev_blob, "dense plan was created without a bound GPU (call hq_init first)");
     static bool attr_set = false;
-    static bool want_db = true;
+    static int want_db = -1;   // HQ_DENSE_DB: unset = per plan (below), 0 = never, 1 = whenever it fits
     if (!attr_set) {
         HQ_CUDA(cudaFuncSetAttribute(dense_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         HQ_CUDA(cudaFuncSetAttribute(dense_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         HQ_CUDA(cudaFuncSetAttribute(dense_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         HQ_CUDA(cudaFuncSetAttribute(dense_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        if (const char* e = getenv("HQ_DENSE_DB")) want_db = atoi(e) != 0;
+        if (const char* e = getenv("HQ_DENSE_DB")) want_db = atoi(e) != 0 ? 1 : 0;
         attr_set = true;
     }
     int maxm = 0;
     for (int i = 0; i < plan->p.nmat; ++i) maxm = std::max(maxm, plan->p.mats[i].m);
     const size_t smem_db = plan->smem + ((size_t)16 << plan->Kt);
-    const bool db = want_db && smem_db <= 227 * 1024;
+    // Which shape?  Measured at 2^30 amplitudes (profiles/r01_s10_microbench.json = 3 CTAs/SM single buffer, r01_s11 = double
+    // buffer): the double buffer wins where one matrix dominates the tile's time (m = 6: 18.8 vs 20.9 ms; a lone m <= 3:
+    // 5.4 vs 5.9 ms) and loses where several small matrices share a launch (m4: 7.5 vs 6.0, m4x2: 12.1 vs 10.4, m3x3: 10.6 vs
+    // 8.8) -- eight warps cannot cover the barriers between matrices.  While a swap kernel is co-resident the double-buffered
+    // shape is the one that leaves it a slot on every SM.
+    const bool db_pays = maxm >= 6 || (plan->p.nmat == 1 && maxm <= 3) || rt().reserved_ctas > 0;
+    const bool db = (want_db < 0 ? db_pays : want_db != 0) && smem_db <= 227 * 1024;
     auto kern = db ? (maxm <= 4 ? dense_kernel<4, true> : dense_kernel<6, true>) : (maxm <= 4 ? dense_kernel<4, false> : dense_kernel<6, false>);
     const size_t smem = db ? smem_db : plan->smem;
     int nb = 0;

@@ -77,6 +77,27 @@ __device__ __forceinline__ void lds_v2u64(uint32_t a, ulonglong2& v) {
 __device__ __forceinline__ void lds_v2f64(uint32_t a, double2& v) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
 }
+// Coefficients m[0..7] of an op, by quarters: need bit 0 -> m[0..3], bit 1 -> m[4..5], bit 2 -> m[6..7]; the others keep
+// whatever they held (no body reads them).
+__device__ __forceinline__ void lds_coeffs(uint32_t a, uint32_t need, double2& m01, double2& m23, double2& m45, double2& m67) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q0, q1, q2;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %9, 1;\n"
+        "setp.ne.u32 q0, t, 0;\n"
+        "and.b32 t, %9, 2;\n"
+        "setp.ne.u32 q1, t, 0;\n"
+        "and.b32 t, %9, 4;\n"
+        "setp.ne.u32 q2, t, 0;\n"
+        "@q0 ld.shared.v2.f64 {%0, %1}, [%8];\n"
+        "@q0 ld.shared.v2.f64 {%2, %3}, [%8+16];\n"
+        "@q1 ld.shared.v2.f64 {%4, %5}, [%8+32];\n"
+        "@q2 ld.shared.v2.f64 {%6, %7}, [%8+48];\n"
+        "}"
+        : "+d"(m01.x), "+d"(m01.y), "+d"(m23.x), "+d"(m23.y), "+d"(m45.x), "+d"(m45.y), "+d"(m67.x), "+d"(m67.y)
+        : "r"(a), "r"(need));
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- in-register gate arithmetic -----------------------------------------------------------------
@@ -204,15 +225,14 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
                 lds_v4(a + 64, nhd);
                 lds_v2u64(a + 80, ncp);
             }
+            double2 m01 = make_double2(0.0, 0.0), m23 = m01, m45 = m01, m67 = m01;
             for (int op = rd.op_begin; op < op_end; ++op) {
                 const uint4 hd = nhd;
                 const ulonglong2 cp = ncp;
                 const uint32_t pa = ops_sa + (uint32_t)op * (uint32_t)sizeof(DevOp);
-                double2 m01, m23, m45, m67;
-                lds_v2f64(pa, m01);
-                lds_v2f64(pa + 16, m23);
-                lds_v2f64(pa + 32, m45);
-                lds_v2f64(pa + 48, m67);
+                // only the coefficient quarters the body reads (flags bits 16..18, set by the planner): butterflies, sign
+                // flips and swaps read none -- the op list is the largest shared-memory consumer of the kernel (ncu)
+                lds_coeffs(pa, hd.z >> 16, m01, m23, m45, m67);
                 {   // next header (the slot after the last op is readable padding, never interpreted)
                     const uint32_t skip = hd.x == CODE_DIAG_RUN ? hd.w : 0u;
                     const uint32_t a = pa + (1u + skip) * (uint32_t)sizeof(DevOp);
@@ -238,9 +258,12 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
                 hq_store_amps_global(P.state + phys, rd.go);
             } else {
                 const uint32_t tout = tb_s[(size_t)(2 * r + 1) * NT + tid];
-                if (rd.flags & 1u) __syncthreads();
+                // Exchanges whose data stays inside each warp's own slice of the tile (same warp qubits before and after:
+                // flags bits 2/3, proven by the planner) need no CTA barrier: the warps of a CTA drift apart and fill each
+                // other's shared-memory and barrier bubbles with FP64 work.
+                if (rd.flags & 1u) { if (rd.flags & 8u) __syncwarp(); else __syncthreads(); }
                 hq_store_amps(tile_s, tout, rd.ro_out);
-                __syncthreads();
+                if (rd.flags & 4u) __syncwarp(); else __syncthreads();
             }
         }
     }
@@ -300,6 +323,19 @@ static bool classify(const hq_gate& g, HostGate& h) {
     else if (is_zero(m[1]) && is_zero(m[2]) && is_zero(m[4]) && is_zero(m[7])) h.kind = OP_RXL;
     else h.kind = OP_GEN;
     return true;
+}
+
+// Which quarters of m[] the kernel must fetch for this op (DevOp::flags bits 16..18): bit 0 = m[0..3], 1 = m[4..5], 2 = m[6..7].
+static uint32_t coeff_need(const DevOp& o) {
+    if (o.code == CODE_DIAG_RUN) return 0;                        // the entries are read by op_diag_run itself
+    if (o.code == CODE_DIAG_T) return (o.flags & 1u) ? 4u : 5u;   // d1 only when d0 == 1
+    switch (o.code / 24) {
+        case OP_GEN: return 7u;
+        case OP_REAL: case OP_RXL: return 1u;
+        case OP_DIAG_R: return 5u;
+        case OP_DIAG_R1: return 4u;
+        default: return 0u;   // swap, Y, sign flip, butterflies: no coefficients
+    }
 }
 
 // Coefficients of the in-place LU update for M = [[a,b],[c,d]]:  {c, d, e = det/d, f = b/d}.
@@ -376,6 +412,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
     {
         std::vector<int> remaining(hg.size());
         for (size_t i = 0; i < hg.size(); ++i) remaining[i] = (int)i;
+        const bool avoid_low_in_round0 = getenv("HQ_ROUND0_LOW_BITS") == nullptr;
         while (!remaining.empty()) {
             Round rd;
             uint64_t blockedX = 0, blockedZ = 0;
@@ -387,6 +424,13 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                 if (h.c1_phys >= 0) q_d |= 1ull << h.c1_phys;
                 if (h.c2_phys >= 0) q_d |= 1ull << h.c2_phys;
                 bool can = !(q_nd & (blockedX | blockedZ)) && !(q_d & blockedX);
+                if (can && !h.diag) {
+                    const int tt = phys_to_tile[h.target_phys];
+                    // Round 0 reads the linear TMA image: a register qubit on tile bits 0..2 would put every lane of a
+                    // quarter-warp on the same 16-byte bank group (8-way conflicts on all 16 loads; ncu: 3x the ideal
+                    // wavefronts over a 4-round launch).  Those gates wait for round 1, which reads the swizzled layout.
+                    if (rounds.empty() && tt < 3 && avoid_low_in_round0) can = false;
+                }
                 if (can && !h.diag) {
                     const int tt = phys_to_tile[h.target_phys];
                     if (std::find(rd.reg.begin(), rd.reg.end(), tt) == rd.reg.end()) {
@@ -401,13 +445,44 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             remaining.swap(rest);
         }
         if (rounds.empty()) rounds.push_back(Round{});
-        for (auto& rd : rounds) {   // pad the register set with the highest free tile bits
-            for (int b = K - 1; b >= 0 && (int)rd.reg.size() < RBITS; --b)
-                if (std::find(rd.reg.begin(), rd.reg.end(), b) == rd.reg.end()) rd.reg.push_back(b);
-            std::sort(rd.reg.begin(), rd.reg.end());
-        }
     }
     const int nrounds = (int)rounds.size();
+    // Warp qubits (thread-id bits 5 and up) of every round.  A round whose warp qubits equal the previous round's exchanges
+    // data only inside each warp, so the barrier between them is a __syncwarp.  Keep them while none is needed as a register
+    // qubit; when they must change, take the candidates that stay clear of the following rounds' targets the longest (ties:
+    // the highest, so that lanes keep the low bits and HBM stores stay contiguous).  Tile bits 0..2 never serve: the swizzle
+    // only rewrites bits 0..2, so avoiding them keeps a warp's slice the same set of positions in the linear (TMA) image and
+    // in the swizzled one.
+    const int nwb = K - RBITS - 5;
+    const bool allow_local = nwb > 0 && getenv("HQ_NO_LOCAL_EXCHANGE") == nullptr;
+    std::vector<std::vector<int>> warp_bits(nrounds);
+    std::vector<char> local_in(nrounds, 0);   // round r reads only what the same warp wrote in round r-1
+    if (allow_local) {
+        auto needs = [&](int r, int b) { return std::find(rounds[r].reg.begin(), rounds[r].reg.end(), b) != rounds[r].reg.end(); };
+        for (int r = 0; r < nrounds; ++r) {
+            bool sticky = r > 0;
+            if (sticky) for (int b : warp_bits[r - 1]) if (needs(r, b)) sticky = false;
+            if (sticky) { warp_bits[r] = warp_bits[r - 1]; local_in[r] = 1; continue; }
+            std::vector<std::pair<int, int>> cand;   // (-survival, -bit)
+            for (int b = 3; b < K; ++b) {
+                if (needs(r, b)) continue;
+                int surv = 0;
+                for (int rr = r + 1; rr < nrounds && !needs(rr, b); ++rr) ++surv;
+                cand.push_back({-surv, -b});
+            }
+            std::sort(cand.begin(), cand.end());
+            for (int i = 0; i < nwb; ++i) warp_bits[r].push_back(-cand[i].second);   // K - 3 - RBITS >= nwb candidates always exist
+            std::sort(warp_bits[r].begin(), warp_bits[r].end());
+        }
+    }
+    for (int r = 0; r < nrounds; ++r) {   // pad the register set with the highest tile bits that are not warp qubits
+        Round& rd = rounds[r];
+        for (int b = K - 1; b >= 0 && (int)rd.reg.size() < RBITS; --b)
+            if (std::find(rd.reg.begin(), rd.reg.end(), b) == rd.reg.end() &&
+                std::find(warp_bits[r].begin(), warp_bits[r].end(), b) == warp_bits[r].end())
+                rd.reg.push_back(b);
+        std::sort(rd.reg.begin(), rd.reg.end());
+    }
     // butterflies leave their scalars behind: one factor for the whole launch, applied with the last round's diagonal run
     std::complex<double> launch_scale(1.0, 0.0);
     bool any_bfly = false;
@@ -536,6 +611,11 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         for (int b = 0; b < K; ++b) if (reg_of_tile[b] < 0) free_bits.push_back(b);
         std::vector<int> tbits;
         const bool is_last = r == nrounds - 1, lin_in = r == 0;
+        if (allow_local) {
+            std::vector<int> lanes_free;
+            for (int b : free_bits) if (std::find(warp_bits[r].begin(), warp_bits[r].end(), b) == warp_bits[r].end()) lanes_free.push_back(b);
+            free_bits.swap(lanes_free);   // the rules below now order the LANE bits only; the warp bits are appended after them
+        }
         if (is_last) {
             tbits = free_bits;
         } else {
@@ -550,6 +630,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             tbits = first;
             for (int b : pref) if (std::find(tbits.begin(), tbits.end(), b) == tbits.end()) tbits.push_back(b);
         }
+        if (allow_local) tbits.insert(tbits.end(), warp_bits[r].begin(), warp_bits[r].end());
 
         DevRound& d = drounds[r];
         std::memset(&d, 0, sizeof(d));
@@ -575,8 +656,10 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             sc.m[1] = sc.m[7] = launch_scale.imag();
             run.push_back(sc);
         }
-        for (DevOp& o : body)   // body index for the kernel's single indexed branch
+        for (DevOp& o : body) {   // body index for the kernel's single indexed branch + which coefficient quarters it reads
             if (o.code < CODE_DIAG_T) o.flags |= (uint32_t)HQ_OP_BODY_INDEX[o.code] << 8;
+            o.flags |= coeff_need(o) << 16;
+        }
         d.op_begin = (int)dops.size();
         if (!run.empty()) {   // the run commutes with every other op of the round (it touches no register bit)
             DevOp hdr{};
@@ -588,12 +671,43 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         dops.insert(dops.end(), body.begin(), body.end());
         d.op_end = (int)dops.size();
         if (trace_plan) {   // developer aid: which bodies does this round execute?
-            fprintf(stderr, "[plan] round %d/%d regs={", r, nrounds);
+            fprintf(stderr, "[plan] round %d/%d%s regs={", r, nrounds, local_in[r] ? " (warp-local in)" : "");
             for (int b = 0; b < RBITS; ++b) fprintf(stderr, "%d%s", rd.reg[b], b + 1 < RBITS ? "," : "} ops:");
             for (int i = d.op_begin; i < d.op_end; ++i) fprintf(stderr, " %u", dops[i].code);
             fprintf(stderr, "\n");
         }
         d.flags = (lin_in && nrounds > 1 ? 1u : 0u) | (is_last ? 2u : 0u);
+    }
+
+    // ---- warp-local exchanges: prove them on the tables just built, then flag them ----
+    // Exchange r -> r+1 is warp-local iff, for every warp, the shared-memory positions it writes at the end of round r are
+    // exactly the positions it reads at the start of round r+1.  Round 0's layout change (linear -> swizzled) needs, in
+    // addition, that the warp reads and writes the same positions within round 0.
+    int nlocal = 0;
+    {
+        auto positions = [&](int r, int which, int warp) {   // which: 0 = read layout, 1 = write layout
+            std::vector<uint16_t> v;
+            v.reserve(32 * R);
+            const uint16_t* ro = which ? drounds[r].ro_out : drounds[r].ro_in;
+            for (int t = warp * 32; t < warp * 32 + 32 && t < NT; ++t)
+                for (int i = 0; i < R; ++i) v.push_back((uint16_t)(tb[(size_t)(2 * r + which) * NT + t] ^ ro[i]));
+            std::sort(v.begin(), v.end());
+            return v;
+        };
+        const int nwarps = (NT + 31) / 32;
+        for (int r = 0; r + 1 < nrounds; ++r) {
+            if (!local_in[r + 1]) continue;
+            bool ok = true;
+            for (int w = 0; w < nwarps && ok; ++w) ok = positions(r, 1, w) == positions(r + 1, 0, w);
+            if (!ok) continue;
+            drounds[r].flags |= 4u;
+            ++nlocal;
+            if (drounds[r].flags & 1u) {
+                bool same = true;
+                for (int w = 0; w < nwarps && same; ++w) same = positions(r, 0, w) == positions(r, 1, w);
+                if (same) drounds[r].flags |= 8u;
+            }
+        }
     }
 
     // ---- tile geometry ----
@@ -605,7 +719,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
 
     auto* plan = new hq_group_plan();
     plan->L = L; plan->K = K; plan->NT = NT; plan->tile_mask = tile_mask;
-    plan->nrounds = nrounds; plan->nops = (int)dops.size(); plan->ngates = (int)hg.size();
+    plan->nrounds = nrounds; plan->nops = (int)dops.size(); plan->ngates = (int)hg.size(); plan->nlocal = nlocal;
     GroupParams& p = plan->p;
     p.ntiles = 1ull << (L - K - popcount64(fixed_mask));
     p.fixed_base = fixed_value;
@@ -710,6 +824,12 @@ extern "C" int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* o
     if (ops) *ops = plan->nops;
     if (grid) *grid = plan->grid;
     if (smem_bytes) *smem_bytes = (int)plan->smem;
+    return HQ_OK;
+}
+
+extern "C" int hq_group_plan_local_exchanges(const hq_group_plan* plan, int* n) {
+    HQ_REQUIRE(plan != nullptr && n != nullptr, "null argument");
+    *n = plan->nlocal;
     return HQ_OK;
 }
 

@@ -59,7 +59,8 @@ struct alignas(16) DevRound {
     uint16_t ro_out[R];   // same for the write layout
     uint64_t go[R];       // physical offset contributed by register index i
     int32_t op_begin, op_end;
-    uint32_t flags;       // bit0: read layout != write layout (extra barrier), bit1: last round -> HBM
+    uint32_t flags;       // bit0: read layout != write layout (extra barrier), bit1: last round -> HBM,
+                          // bit2: the exchange after this round stays inside each warp (__syncwarp), bit3: so does bit0's
     uint32_t pad;
 };
 
@@ -88,6 +89,7 @@ struct hq_group_plan {
     int L = 0, K = 0, NT = 0;
     uint64_t tile_mask = 0;
     int nrounds = 0, nops = 0, ngates = 0;
+    int nlocal = 0;                       // exchanges between rounds that need only a warp-level barrier
     mutable int grid = 0;
     size_t smem = 0;
     std::vector<unsigned char> blob;      // host image of the device tables (run_off | rounds | ops | gt | tb)

@@ -86,6 +86,7 @@ int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed_mask, uint
 int hq_group_plan_launch(const hq_group_plan* plan, void* state, int on_comm_stream);
 int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* ops, int* grid, int* smem_bytes);
 int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes);   /* size of the uploaded device tables */
+int hq_group_plan_local_exchanges(const hq_group_plan* plan, int* n);   /* round exchanges done with a warp-level barrier */
 int hq_group_plan_destroy(hq_group_plan* plan);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 

@@ -115,6 +115,30 @@ def test_reference_goldens_byte_exact(gpu_runtime, golden_dir, name):
     c.close()
 
 
+@pytest.mark.parametrize("name,backend", [("supremacy_26", "b1"), ("quantum_volume_24", "b3"), ("qaoa_26", "b1"),
+                                          ("basis_change_24", "b3"), ("supremacy_28", "b3")])
+def test_same_dump_as_reference_build(gpu_runtime, tmp_path, name, backend):
+    """Families whose upstream goldens are lost: our printState text vs the text printed by the reference's
+    OWN binary (oracle/_ref/hyquas_ref_b1 = OShareMem build, b3 = TransMM build, compiled from /root/reference by
+    oracle/Makefile) on the same circuit on this GPU, under scripts/compare.py's rule with a hard 1e-10 threshold."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "hyquas_ref_" + backend)
+    if not os.path.exists(exe):
+        pytest.skip("reference build not present (oracle/Makefile ref needs /root/reference)")
+    text = C.generate(name)
+    qasm = tmp_path / (name + ".qasm")
+    qasm.write_text(text)
+    r = subprocess.run([exe, str(qasm)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    ref_dump = "".join(l + "\n" for l in r.stdout.splitlines() if re.match(r"^\d+ \d\.\d+: ", l))
+    assert ref_dump.count("\n") >= 128
+    c = _run(gpu_runtime, text)
+    ok, err = O.compare_dumps(ref_dump, c.dump())
+    assert ok, err
+    c.close()
+
+
 @pytest.mark.parametrize("name", ["supremacy_30", "qaoa_30"])
 def test_full_size_round_trip(gpu_runtime, name):
     """BASELINE size (30 qubits, 16 GiB): U^dagger U |0> = |0>, norm preserved -- properties that need no oracle."""

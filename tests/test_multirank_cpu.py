@@ -1,4 +1,4 @@
-"""world_size-2/4 `gloo` tests of the multi-GPU path's host logic (no GPU): stage split, per-rank lowering, swap plan,
+"""world_size-2/4/8 `gloo` tests of the multi-GPU path's host logic (no GPU): stage split, per-rank lowering, swap plan,
 per-chunk overlap groups, final layout.  See tests/multirank_worker.py for what each rank does."""
 import os
 import socket
@@ -33,7 +33,7 @@ def _run(world, text, env=None):
 @pytest.mark.parametrize("any_bit", ["0", "1"])
 @pytest.mark.parametrize("world,name", [(2, "qft_14"), (2, "supremacy_14"), (2, "adder_14"),
                                         (4, "quantum_volume_14"), (4, "hidden_shift_14"), (4, "basis_change_14"),
-                                        (4, "bv_15")])
+                                        (4, "bv_15"), (8, "qaoa_16"), (8, "adder_16"), (8, "supremacy_15")])
 def test_sharded_schedule_matches_oracle(world, name, any_bit):
     """any_bit=0: swaps trade the top k local positions (nccl transport); 1: any position >= 5 (p2p transport)."""
     text = C.generate(name)

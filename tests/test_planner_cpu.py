@@ -48,6 +48,32 @@ def test_group_plan_tables_match_oracle(n, K, seed):
     assert np.max(np.abs(st - want)) < 1e-13
 
 
+def test_warp_local_exchanges_are_found_and_optional(monkeypatch):
+    """H on 12 qubits, K = 12: rounds {0..3}, {4..7}, {8..11}.  The warp qubits of round 0 survive round 1, so that exchange
+    needs only a warp-level barrier (the planner proves it on its own tables); the next one changes the warp qubits.
+    HQ_NO_LOCAL_EXCHANGE switches the feature off; the tables compute the same state either way."""
+    n = 14
+    gates = [O.OGate("h", q) for q in range(12)] + [O.OGate("t", q) for q in range(12)] + [O.OGate("h", q) for q in range(12)]
+    res = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("HQ_NO_LOCAL_EXCHANGE", "1")
+        plan = ctypes.c_void_p()
+        check(lib.hq_group_plan_create(n, 0xFFF, pack(gates), len(gates), ctypes.byref(plan)))
+        nloc, rounds = ctypes.c_int(), ctypes.c_int()
+        check(lib.hq_group_plan_local_exchanges(plan, ctypes.byref(nloc)))
+        check(lib.hq_group_plan_info(plan, ctypes.byref(rounds), None, None, None))
+        st = random_state(n, 3)
+        want = st.copy()
+        O.apply(want, n, gates)
+        check(lib.hq_debug_group_plan_emulate(plan, st.ctypes.data))
+        lib.hq_group_plan_destroy(plan)
+        assert np.max(np.abs(st - want)) < 1e-13
+        res.append((nloc.value, rounds.value))
+    assert res[0][1] >= 3 and res[0][0] >= 1
+    assert res[1][0] == 0
+
+
 def test_group_plan_rejects_target_outside_tile():
     g = O.OGate("h", 11)
     plan = ctypes.c_void_p()
