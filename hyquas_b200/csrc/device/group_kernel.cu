@@ -71,32 +71,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 __device__ __forceinline__ void lds_v4(uint32_t a, uint4& v) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
 }
+__device__ __forceinline__ void lds_u32(uint32_t a, uint32_t& v) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); }
 __device__ __forceinline__ void lds_v2u64(uint32_t a, ulonglong2& v) {
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
 }
 __device__ __forceinline__ void lds_v2f64(uint32_t a, double2& v) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
-}
-// Coefficients m[0..7] of an op, by quarters: need bit 0 -> m[0..3], bit 1 -> m[4..5], bit 2 -> m[6..7]; the others keep
-// whatever they held (no body reads them).
-__device__ __forceinline__ void lds_coeffs(uint32_t a, uint32_t need, double2& m01, double2& m23, double2& m45, double2& m67) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q0, q1, q2;\n"
-        ".reg .b32 t;\n"
-        "and.b32 t, %9, 1;\n"
-        "setp.ne.u32 q0, t, 0;\n"
-        "and.b32 t, %9, 2;\n"
-        "setp.ne.u32 q1, t, 0;\n"
-        "and.b32 t, %9, 4;\n"
-        "setp.ne.u32 q2, t, 0;\n"
-        "@q0 ld.shared.v2.f64 {%0, %1}, [%8];\n"
-        "@q0 ld.shared.v2.f64 {%2, %3}, [%8+16];\n"
-        "@q1 ld.shared.v2.f64 {%4, %5}, [%8+32];\n"
-        "@q2 ld.shared.v2.f64 {%6, %7}, [%8+48];\n"
-        "}"
-        : "+d"(m01.x), "+d"(m01.y), "+d"(m23.x), "+d"(m23.y), "+d"(m45.x), "+d"(m45.y), "+d"(m67.x), "+d"(m67.y)
-        : "r"(a), "r"(need));
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -215,43 +195,43 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
                 if (tn < P.ntiles && tid < 32) issue_tile_load<K>(P, tn, tile, bar, tbase_s, tid);
             }
 
-            // Op headers (code, masks) are read one op AHEAD, while the current body runs; the eight coefficients are
-            // requested first thing in the iteration, so their latency hides behind the predicate checks and the jump.
-            const int op_end = rd.op_end;
+            // The op loop.  A plain op (register target, no predicate outside the registers: most single-qubit gates) costs
+            // one header read-ahead, one flag test and the indexed jump into its body; the bodies fetch their own
+            // coefficients.  Everything else -- predicate masks, diagonal gates on non-register bits, diagonal runs --
+            // hides behind ONE "special" flag bit.  The header is read one op AHEAD, while the current body runs.
+            uint32_t pa = ops_sa + (uint32_t)rd.op_begin * (uint32_t)sizeof(DevOp);
+            const uint32_t pa_end = ops_sa + (uint32_t)rd.op_end * (uint32_t)sizeof(DevOp);
             uint4 nhd;         // code, creg, flags, aux
-            ulonglong2 ncp;    // cphys, tphys
-            {
-                const uint32_t a = ops_sa + (uint32_t)rd.op_begin * (uint32_t)sizeof(DevOp);
-                lds_v4(a + 64, nhd);
-                lds_v2u64(a + 80, ncp);
-            }
-            double2 m01 = make_double2(0.0, 0.0), m23 = m01, m45 = m01, m67 = m01;
-            for (int op = rd.op_begin; op < op_end; ++op) {
+            lds_v4(pa + 64, nhd);
+            while (pa < pa_end) {
                 const uint4 hd = nhd;
-                const ulonglong2 cp = ncp;
-                const uint32_t pa = ops_sa + (uint32_t)op * (uint32_t)sizeof(DevOp);
-                // only the coefficient quarters the body reads (flags bits 16..18, set by the planner): butterflies, sign
-                // flips and swaps read none -- the op list is the largest shared-memory consumer of the kernel (ncu)
-                lds_coeffs(pa, hd.z >> 16, m01, m23, m45, m67);
-                {   // next header (the slot after the last op is readable padding, never interpreted)
-                    const uint32_t skip = hd.x == CODE_DIAG_RUN ? hd.w : 0u;
-                    const uint32_t a = pa + (1u + skip) * (uint32_t)sizeof(DevOp);
-                    lds_v4(a + 64, nhd);
-                    lds_v2u64(a + 80, ncp);
+                const uint32_t cur = pa;
+                pa += (uint32_t)sizeof(DevOp);
+                lds_v4(pa + 64, nhd);   // (the slot after the last op is readable padding, never interpreted)
+                if (hd.z & 4u) {
+                    if (hd.x == CODE_DIAG_RUN) {
+                        uint32_t n;   // entry count: re-read here rather than kept live through every plain op (a spill otherwise)
+                        lds_u32(cur + 76, n);
+                        pa += n * (uint32_t)sizeof(DevOp);
+                        lds_v4(pa + 64, nhd);   // the header read ahead above was the run's first entry: fetch the real next op
+                        op_diag_run(ops_s + (cur - ops_sa) / (uint32_t)sizeof(DevOp) + 1, (int)n, phys, hd.y);
+                        continue;
+                    }
+                    // predicate masks (cphys, tphys) are not read ahead: four more registers carried around the loop push
+                    // ptxas into spilling at the 128-register cap
+                    ulonglong2 cp;
+                    lds_v2u64(cur + 80, cp);
+                    if ((phys & cp.x) != cp.x) continue;
+                    if (hd.x == CODE_DIAG_T) {
+                        const bool hi = (cp.y == 0) || (phys & cp.y);
+                        if (!hi && (hd.z & 1u)) continue;
+                        double2 d;
+                        lds_v2f64(cur + (hi ? 48u : 0u), d);
+                        hq_cmul_masked(d.x, d.y, hd.y);
+                        continue;
+                    }
                 }
-                if (hd.x == CODE_DIAG_RUN) {
-                    op_diag_run(ops_s + op + 1, (int)hd.w, phys, hd.y);
-                    op += (int)hd.w;
-                    continue;
-                }
-                if ((phys & cp.x) != cp.x) continue;
-                if (hd.x == CODE_DIAG_T) {
-                    const bool hi = (cp.y == 0) || (phys & cp.y);
-                    if (!hi && (hd.z & 1u)) continue;
-                    hq_cmul_masked(hi ? m67.x : m01.x, hi ? m67.y : m01.y, hd.y);
-                } else {
-                    hq_apply_op((hd.z >> 8) & 0xffu, hd.y, m01.x, m01.y, m23.x, m23.y, m45.x, m45.y, m67.x, m67.y);
-                }
+                hq_apply_op(hd.z >> 16, hd.y, cur);
             }
 
             if (last) {
@@ -323,19 +303,6 @@ static bool classify(const hq_gate& g, HostGate& h) {
     else if (is_zero(m[1]) && is_zero(m[2]) && is_zero(m[4]) && is_zero(m[7])) h.kind = OP_RXL;
     else h.kind = OP_GEN;
     return true;
-}
-
-// Which quarters of m[] the kernel must fetch for this op (DevOp::flags bits 16..18): bit 0 = m[0..3], 1 = m[4..5], 2 = m[6..7].
-static uint32_t coeff_need(const DevOp& o) {
-    if (o.code == CODE_DIAG_RUN) return 0;                        // the entries are read by op_diag_run itself
-    if (o.code == CODE_DIAG_T) return (o.flags & 1u) ? 4u : 5u;   // d1 only when d0 == 1
-    switch (o.code / 24) {
-        case OP_GEN: return 7u;
-        case OP_REAL: case OP_RXL: return 1u;
-        case OP_DIAG_R: return 5u;
-        case OP_DIAG_R1: return 4u;
-        default: return 0u;   // swap, Y, sign flip, butterflies: no coefficients
-    }
 }
 
 // Coefficients of the in-place LU update for M = [[a,b],[c,d]]:  {c, d, e = det/d, f = b/d}.
@@ -656,15 +623,16 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             sc.m[1] = sc.m[7] = launch_scale.imag();
             run.push_back(sc);
         }
-        for (DevOp& o : body) {   // body index for the kernel's single indexed branch + which coefficient quarters it reads
-            if (o.code < CODE_DIAG_T) o.flags |= (uint32_t)HQ_OP_BODY_INDEX[o.code] << 8;
-            o.flags |= coeff_need(o) << 16;
+        for (DevOp& o : body) {   // body index for the kernel's single indexed branch; "special" bit (see the op loop)
+            if (o.code < CODE_DIAG_T) o.flags |= (uint32_t)HQ_OP_BODY_INDEX[o.code] << 16;
+            if ((o.cphys | o.tphys) || o.code >= CODE_DIAG_T) o.flags |= 4u;
         }
         d.op_begin = (int)dops.size();
         if (!run.empty()) {   // the run commutes with every other op of the round (it touches no register bit)
             DevOp hdr{};
             hdr.code = CODE_DIAG_RUN;
             hdr.aux = (uint32_t)run.size();
+            hdr.flags = 4u;
             dops.push_back(hdr);
             dops.insert(dops.end(), run.begin(), run.end());
         }

@@ -47,7 +47,8 @@ struct alignas(16) DevOp {
     double m[8];       // row-major 2x2 (re, im); diagonal ops use m[0..1] = d0, m[6..7] = d1
     uint32_t code;     // op_code(kind, tbit, cbc) / CODE_DIAG_T / CODE_DIAG_RUN
     uint32_t creg;     // all register-index control bits
-    uint32_t flags;    // bit0: d0 == 1 (the "lo" half of a diagonal is untouched); bits 8..15: body index of hq_apply_op
+    uint32_t flags;    // bit0: d0 == 1 (the "lo" half of a diagonal is untouched); bit2: "special" = has predicate masks, or is a DIAG_T / DIAG_RUN
+                       // (top-level ops); bits 16..23: body index of hq_apply_op
     uint32_t aux;      // CODE_DIAG_RUN: number of entries that follow
     uint64_t cphys;    // controls outside the registers, as a mask over the physical local index
     uint64_t tphys;    // diagonal ops with a non-register target: its physical bit (0 = scalar, always d1)

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <fstream>
 
@@ -11,27 +12,29 @@ Evaluator* Evaluator::getInstance() {
 }
 
 Evaluator::Evaluator() {
-    // Defaults = this pool's B200, FP64, measured with tools/microbench.py at 2^30 amplitudes (profiles/r01_s4_microbench.json):
+    // Defaults = this pool's B200, FP64, measured with tools/microbench.py at 2^30 amplitudes (profiles/r01_s16_microbench.json):
     // a gate-group launch of G same-type gates takes  max(sweep, groupBaseMs30 + G * gate cost + extra rounds * roundMs30);
     // a fused dense launch takes  max(sweep, denseBaseMs30 + sum of per-matrix costs).  tools/calibrate.py rewrites them
     // from a fresh microbenchmark run ($HYQUAS_PARAM_FILE).
-    hbmGBs = 5940.0;        // one in-place sweep (16 B read + 16 B written per amplitude): 5.78 ms per 2^30
+    hbmGBs = 5915.0;        // one in-place sweep (16 B read + 16 B written per amplitude): 5.8 ms per 2^30
     launchMs = 0.01;
     nvlinkGBs = 700.0;
-    groupBaseMs30 = 1.9;
+    groupBaseMs30 = 2.6;
     denseBaseMs30 = 0.6;
-    roundMs30 = 3.2;
-    for (auto& g : gateNs) g = 0.40;
+    circuitFactor = 1.45;
+    roundMs30 = 2.0;        // h_x96_12q gives 1.2; groups of real circuits (predicates on lane bits, uneven rounds) fit 2.0
+    for (auto& g : gateNs) g = 0.35;
     auto set = [&](GateType t, double ms30) { gateNs[int(t)] = ms30; };
-    set(GateType::H, 0.35); set(GateType::RY, 0.37); set(GateType::RX, 0.50);
-    set(GateType::U2, 0.75); set(GateType::U3, 0.75);
-    // diag(1,d) gates merge into per-register-bit diagonal runs (one factor per thread): ~0.1 ms each
-    set(GateType::T, 0.11); set(GateType::TDG, 0.11); set(GateType::S, 0.11); set(GateType::SDG, 0.11); set(GateType::U1, 0.11);
-    set(GateType::RZ, 0.45); set(GateType::Z, 0.11); set(GateType::X, 0.37); set(GateType::Y, 0.37);
-    set(GateType::CZ, 0.13); set(GateType::CU1, 0.13); set(GateType::CRZ, 0.35);
-    set(GateType::CNOT, 0.27); set(GateType::CY, 0.30); set(GateType::CCX, 0.20);
-    set(GateType::CRX, 0.45); set(GateType::CRY, 0.40);
-    const double dense[8] = {2.7, 2.7, 2.7, 2.7, 5.4, 9.7, 20.1, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
+    // H prices every butterfly (H, RX/RY(+-pi/2): two FP64 adds per amplitude); see perfPerGate(gates)
+    set(GateType::H, 0.18); set(GateType::RY, 0.35); set(GateType::RX, 0.43);
+    set(GateType::U2, 0.68); set(GateType::U3, 0.68);
+    // diag(1,d) gates merge into per-register-bit diagonal runs (one factor per thread)
+    set(GateType::T, 0.09); set(GateType::TDG, 0.09); set(GateType::S, 0.09); set(GateType::SDG, 0.09); set(GateType::U1, 0.09);
+    set(GateType::RZ, 0.15); set(GateType::Z, 0.09); set(GateType::X, 0.43); set(GateType::Y, 0.43);
+    set(GateType::CZ, 0.10); set(GateType::CU1, 0.10); set(GateType::CRZ, 0.25);
+    set(GateType::CNOT, 0.25); set(GateType::CY, 0.27); set(GateType::CCX, 0.25);
+    set(GateType::CRX, 0.33); set(GateType::CRY, 0.33);
+    const double dense[8] = {2.75, 2.75, 2.75, 2.75, 5.0, 9.7, 18.3, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
     for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
 }
 
@@ -52,6 +55,7 @@ void Evaluator::loadParam(int) {
         else if (key == "launch_ms") in >> launchMs;
         else if (key == "nvlink_gbs") in >> nvlinkGBs;
         else if (key == "round_ms30") in >> roundMs30;
+        else if (key == "circuit_factor") in >> circuitFactor;
         else if (key == "group_base_ms30") in >> groupBaseMs30;
         else if (key == "dense_base_ms30") in >> denseBaseMs30;
         else if (key == "gate") { int i; double v; in >> i >> v; if (i >= 0 && i < 32) gateNs[i] = v; }
@@ -66,17 +70,33 @@ double Evaluator::perfPerGate(int numQubits, const std::vector<GateType>& types)
     return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
 }
 
+// alpha * [[1, p], [q, -p q]] with p, q both in {+-1} or both in {+-i}, uncontrolled: the tile kernel's butterfly class
+// (same test as classify() in device/group_kernel.cu): H, RX(+-pi/2), RY(+-pi/2) whatever their type tag says.
+static bool isButterfly(const Gate& g) {
+    if (g.controlQubit != -1 || g.controlQubit2 != -1) return false;
+    typedef std::complex<double> C;
+    const C a(g.mat[0][0].x, g.mat[0][0].y), b(g.mat[0][1].x, g.mat[0][1].y), c(g.mat[1][0].x, g.mat[1][0].y), d(g.mat[1][1].x, g.mat[1][1].y);
+    if (std::abs(a) < 0.5) return false;
+    const C p = b / a, q = c / a, r = d / a;
+    auto unit = [](C z, bool imag) { return std::abs(std::abs(imag ? z.imag() : z.real()) - 1.0) < 1e-14 && std::abs(imag ? z.real() : z.imag()) < 1e-14; };
+    return ((unit(p, false) && unit(q, false)) || (unit(p, true) && unit(q, true))) && std::abs(r + p * q) < 1e-14;
+}
+
 // With the gates at hand the number of register rounds can be bounded from below: a round holds 4 register qubits.
 double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
     loadParam(numQubits);
     double compute = groupBaseMs30;
     qindex targets = 0;
     for (const Gate& g : gates) {
-        compute += gateNs[int(g.type) & 31];
+        compute += isButterfly(g) ? gateNs[int(GateType::H)] : gateNs[int(g.type) & 31];
         if (!g.isDiagonal()) targets |= qindex(1) << g.targetQubit;
     }
     const int rounds = std::max(1, (bitCount(targets) + 3) / 4);
     compute += roundMs30 * (rounds - 1);
+    // The per-gate constants are measured with every operand on a register qubit (tools/microbench.py); in groups cut from real
+    // circuits controls and diagonal targets land on lane bits and rounds are uneven: the ten tile-kernel launches of
+    // supremacy_30 fit  base + 1.45 * (gates + rounds)  within 12 % (profiles/r01_s16_bench_supremacy30_group.json).
+    compute = groupBaseMs30 + circuitFactor * (compute - groupBaseMs30);
     return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
 }
 

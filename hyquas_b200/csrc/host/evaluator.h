@@ -35,6 +35,7 @@ public:
     double groupBaseMs30;                   // fixed part of a gate-group launch that does not overlap the sweep
     double denseBaseMs30;                   // same for the fused dense kernel
     double roundMs30;                       // cost of one extra register round per 2^30 amplitudes, ms
+    double circuitFactor;                   // in-circuit / microbenchmark cost ratio of the tile kernel's gate work (fit)
     double denseMs30[8];                    // fused dense kernel, per 2^30 amplitudes, indexed by matrix qubits
     double launchMs;                        // fixed per-launch overhead
 private:

@@ -24,8 +24,8 @@ def run_ptx(lines, regs, creg, m):
     def val(tok):
         tok = tok.strip()
         if tok.startswith("%"):
-            k = int(tok[1:])
-            return float(creg) if k == 1 else m[k - 2]
+            assert tok == "%1"
+            return float(creg)
         if tok.startswith("0d"):
             return float(np.array([int(tok[2:], 16)], dtype=np.uint64).view(np.float64)[0])
         if tok.startswith("0x"):
@@ -42,6 +42,12 @@ def run_ptx(lines, regs, creg, m):
             p, line = line.split(" ", 1)
             guard = pred[p[1:]]
         op, rest = line.split(" ", 1)
+        if op == "ld.shared.v2.f64":   # {hqm2j, hqm2j+1}, [%2+16j]: the op's coefficients, as the planner stored them
+            mm = re.fullmatch(r"\{(hqm\d), (hqm\d)\}, \[%2\+(\d+)\]", rest)
+            j = int(mm.group(3)) // 8
+            assert mm.group(1) == f"hqm{j}" and mm.group(2) == f"hqm{j + 1}" and guard
+            regs[mm.group(1)], regs[mm.group(2)] = m[j], m[j + 1]
+            continue
         args = [a.strip() for a in rest.split(",")]
         if not guard:
             continue

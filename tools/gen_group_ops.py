@@ -9,7 +9,10 @@ updates them in place, so a gate costs its FP64 instructions and nothing else.
 
 All op bodies live in ONE asm statement behind a single `brx.idx` jump table (a C++ switch over the same bodies compiled
 to a 7-deep tree of compare+branch per gate).  Operands of that statement are fixed:
-    %0 = body index, %1 = register-index control mask (creg), %2..%9 = the op's eight coefficients m[0..7].
+    %0 = body index, %1 = register-index control mask (creg), %2 = shared-memory address of the op's coefficients m[0..7].
+Each body loads the coefficients it reads (none for butterflies, sign flips, swaps, Y) into registers that live only inside
+the body: the op list is the kernel's largest shared-memory consumer (ncu), and coefficient registers that are live around
+the op loop cost spills at the 128-register cap.
 
     python tools/gen_group_ops.py 4 > hyquas_b200/csrc/device/group_ops_gen_r4.inc     (argument = register qubits per thread)
 
@@ -28,7 +31,8 @@ GENERIC_ONLY = {"GEN", "REAL", "RXL", "YL"}   # single-control cases are routed 
 NO_CONTROL = {k for k in KINDS if k.startswith("BF")}   # butterflies defer their scale: uncontrolled only
 # butterfly variants: M = alpha * [[1, p], [q, -p*q]], (p, q) both real or both imaginary units
 BF_PQ = [(1, 1), (1, -1), (-1, 1), (-1, -1), (1j, 1j), (1j, -1j), (-1j, 1j), (-1j, -1j)]
-M = {f"m{i}": f"%{i + 2}" for i in range(8)}
+M = {f"m{i}": f"hqm{i}" for i in range(8)}
+COEFF_ADDR = "%2"
 CREG = "%1"
 NEG = "0x8000000000000000"
 TWO = "0d4000000000000000"
@@ -133,12 +137,15 @@ def pair_body(kind, lo, hi):
 
 
 NEGS_NEEDED = {"RXL": [0, 3], "GEN": [1, 3, 5, 7], "DIAG_R1": [7], "DIAG_R": [1, 7]}
+# coefficient pairs (m[2j], m[2j+1]) a body reads: one 16-byte shared load each
+COEFF_PAIRS = {"GEN": [0, 1, 2, 3], "REAL": [0, 1], "RXL": [0, 1], "DIAG_R": [0, 3], "DIAG_R1": [3]}
 
 
 def body_lines(kind, tb, cbc, rbits):
     """Straight-line PTX of one dispatch target: `kind` on target register bit tb with control case cbc."""
     R = 1 << rbits
-    out = [f"neg.f64 hqn{i}, {M[f'm{i}']};" for i in NEGS_NEEDED.get(kind, [])]
+    out = [f"ld.shared.v2.f64 {{hqm{2 * j}, hqm{2 * j + 1}}}, [{COEFF_ADDR}+{16 * j}];" for j in COEFF_PAIRS.get(kind, [])]
+    out += [f"neg.f64 hqn{i}, {M[f'm{i}']};" for i in NEGS_NEEDED.get(kind, [])]
     for lo, hi in pairs(tb, R):
         if 1 <= cbc <= 4 and not (lo >> (cbc - 1)) & 1:
             continue
@@ -235,10 +242,9 @@ def main():
     assert len(cat) < 255
     print("static const unsigned char HQ_OP_BODY_INDEX[] = {" + ", ".join(str(v) for v in table) + "};")
     print("// one jump, one body: `body` is HQ_OP_BODY_INDEX[code], warp-uniform")
-    print("__device__ __forceinline__ void hq_apply_op(uint32_t body, uint32_t creg, double m0, double m1, double m2, double m3,")
-    print("                                            double m4, double m5, double m6, double m7) {")
+    print("__device__ __forceinline__ void hq_apply_op(uint32_t body, uint32_t creg, uint32_t coeff_addr) {")
     print("    asm volatile(\"{\\n\"")
-    print('        ".reg .f64 hqt, hqu, hqn0, hqn1, hqn3, hqn5, hqn7;\\n"')
+    print('        ".reg .f64 hqt, hqu, hqn0, hqn1, hqn3, hqn5, hqn7, hqm<8>;\\n"')
     print('        ".reg .pred hqp;\\n"')
     print('        ".reg .b32 hqx;\\n"')
     labels = ", ".join(f"HQB{i}" for i in range(len(cat)))
@@ -250,7 +256,7 @@ def main():
             print(f'        "{l}\\n"')
         print('        "bra.uni HQEND;\\n"')
     print('        "HQEND:\\n"')
-    print('        "}" :: "r"(body), "r"(creg), "d"(m0), "d"(m1), "d"(m2), "d"(m3), "d"(m4), "d"(m5), "d"(m6), "d"(m7));')
+    print('        "}" :: "r"(body), "r"(creg), "r"(coeff_addr) : "memory");')
     print("}")
     print("// clang-format on")
 
