@@ -97,17 +97,21 @@ namespace hq {
 // A run of diagonal gates none of which touches a register bit: every amplitude of the thread gets the same factor.
 // With creg != 0 the factor applies only to the amplitudes whose register-index bits creg are all 1: every diagonal gate
 // with one operand on a register bit and the others elsewhere (the cu1 ladder of a QFT, CZ / CRZ fans) joins such a run.
-__device__ __forceinline__ void op_diag_run(const DevOp* entries, int n, uint64_t phys, uint32_t creg) {
+__device__ __forceinline__ void op_diag_run(uint32_t entries_sa, int n, uint64_t phys, uint32_t creg) {
     double fr = 1.0, fi = 0.0;
     bool any = false;
-    for (int e = 0; e < n; ++e) {
-        const DevOp& o = entries[e];
-        if ((phys & o.cphys) != o.cphys) continue;
-        const bool hi = (o.tphys == 0) || (phys & o.tphys);
-        if (!hi && (o.flags & 1u)) continue;
-        const double dr = hi ? o.m[6] : o.m[0], di = hi ? o.m[7] : o.m[1];
-        const double nr = fma(-fi, di, fr * dr);
-        fi = fma(fi, dr, fr * di);
+    for (int e = 0; e < n; ++e, entries_sa += (uint32_t)sizeof(DevOp)) {   // entries are read by shared address: no generic pointer kept live
+        ulonglong2 cp;      // cphys, tphys
+        lds_v2u64(entries_sa + 80, cp);
+        if ((phys & cp.x) != cp.x) continue;
+        const bool hi = (cp.y == 0) || (phys & cp.y);
+        uint32_t flags;
+        lds_u32(entries_sa + 72, flags);
+        if (!hi && (flags & 1u)) continue;
+        double2 d;
+        lds_v2f64(entries_sa + (hi ? 48u : 0u), d);
+        const double nr = fma(-fi, d.y, fr * d.x);
+        fi = fma(fi, d.x, fr * d.y);
         fr = nr;
         any = true;
     }
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(1 << (K - RBITS), MINB) group_kernel(const __g
                         lds_u32(cur + 76, n);
                         pa += n * (uint32_t)sizeof(DevOp);
                         lds_v4(pa + 64, nhd);   // the header read ahead above was the run's first entry: fetch the real next op
-                        op_diag_run(ops_s + (cur - ops_sa) / (uint32_t)sizeof(DevOp) + 1, (int)n, phys, hd.y);
+                        op_diag_run(cur + (uint32_t)sizeof(DevOp), (int)n, phys, hd.y);
                         continue;
                     }
                     // predicate masks (cphys, tphys) are not read ahead: four more registers carried around the loop push

@@ -38,6 +38,11 @@ struct Runtime {
     int tile_bits = 12;               // K of the gate-group kernel
     int reserved_ctas = 0;            // CTAs of a swap kernel in flight on the comm stream (one per SM)
     bool relaxed_regs = false;        // trade resident CTAs for registers in the gate-group kernel
+    // the last state vector freed, kept for the next hq_state_alloc of the same size: cudaMalloc + cudaFree of 16 GiB cost
+    // ~35 ms per Circuit::run (bench e2e breakdown), more than two sweeps of the state.  HQ_STATE_CACHE=0 turns it off.
+    void* cached_state = nullptr;
+    size_t cached_bytes = 0;
+    bool state_cache = true;
 };
 Runtime& rt();
 

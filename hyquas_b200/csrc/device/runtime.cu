@@ -2,6 +2,7 @@
 // host<->device amplitude transfer, single-amplitude fetch, on-device threshold scan and norm.
 // Stands in for MyGlobalVars::init (src/utils.cpp:17-60) and kernelInit / kernelDeviceToHost /
 // kernelGetAmp / kernelDestroy (src/kernelSimple.cu:9-37,518-530) of the reference.
+#include <map>
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -97,8 +98,15 @@ extern "C" int hq_init(int device) {
         if (k >= 10 && k <= 12) r.tile_bits = k;
     }
     if (const char* e = getenv("HQ_RELAXED_REGS")) r.relaxed_regs = atoi(e) != 0;
+    if (const char* e = getenv("HQ_STATE_CACHE")) r.state_cache = atoi(e) != 0;
     r.ready = true;
     return HQ_OK;
+}
+
+// live state allocations made by hq_state_alloc -> their size (hq_state_free needs it to offer the buffer to the cache)
+static std::map<void*, size_t>& rt_state_sizes() {
+    static std::map<void*, size_t> m;
+    return m;
 }
 
 extern "C" int hq_shutdown(void) {
@@ -106,6 +114,10 @@ extern "C" int hq_shutdown(void) {
     if (!r.ready) return HQ_OK;
     cudaStreamSynchronize(r.compute);
     cudaStreamSynchronize(r.comm);
+    if (r.cached_state) {
+        rt_state_sizes().erase(r.cached_state);
+        cudaFree(r.cached_state);
+    }
     cudaEventDestroy(r.t0);
     cudaEventDestroy(r.t1);
     cudaStreamDestroy(r.compute);
@@ -134,12 +146,41 @@ extern "C" int hq_device_info(char* name, size_t cap, int* sm_count, size_t* tot
 extern "C" int hq_state_alloc(int L, void** state) {
     HQ_REQUIRE(rt().ready, "hq_init() has not been called");
     HQ_REQUIRE(state != nullptr && L >= 1 && L <= 40, "bad arguments to hq_state_alloc");
-    HQ_CUDA(cudaMalloc(state, sizeof(double2) << L));
+    const size_t bytes = sizeof(double2) << L;
+    Runtime& r = rt();
+    if (r.cached_state) {
+        if (r.cached_bytes == bytes) {
+            *state = r.cached_state;
+            r.cached_state = nullptr;
+            r.cached_bytes = 0;
+            return HQ_OK;
+        }
+        HQ_CUDA(cudaFree(r.cached_state));   // wrong size: give it back before asking for more
+        r.cached_state = nullptr;
+        r.cached_bytes = 0;
+    }
+    HQ_CUDA(cudaMalloc(state, bytes));
+    rt_state_sizes()[*state] = bytes;
     return HQ_OK;
 }
 
 extern "C" int hq_state_free(void* state) {
-    if (state) HQ_CUDA(cudaFree(state));
+    if (!state) return HQ_OK;
+    Runtime& r = rt();
+    auto& sizes = rt_state_sizes();
+    auto it = sizes.find(state);
+    if (r.ready && r.state_cache && it != sizes.end()) {
+        HQ_CUDA(cudaStreamSynchronize(r.compute));   // cudaFree would have synchronised; keep that guarantee
+        if (r.cached_state) {
+            sizes.erase(r.cached_state);
+            HQ_CUDA(cudaFree(r.cached_state));
+        }
+        r.cached_state = state;
+        r.cached_bytes = it->second;
+        return HQ_OK;
+    }
+    if (it != sizes.end()) sizes.erase(it);
+    HQ_CUDA(cudaFree(state));
     return HQ_OK;
 }
 

@@ -112,8 +112,9 @@ size_t Circuit::planBytes() const {
             for (const auto& gg : *groups)
                 for (void* p : gg.plans) {
                     int bytes = 0;
-                    hq_group_plan_table_bytes(static_cast<hq_group_plan*>(p), &bytes);
-                    total += bytes;
+                    if (gg.backend == Backend::BLAS) hq_dense_plan_info(static_cast<hq_dense_plan*>(p), nullptr, nullptr, nullptr, nullptr, &bytes);
+                    else hq_group_plan_table_bytes(static_cast<hq_group_plan*>(p), &bytes);
+                    total += (size_t)std::max(bytes, 0);
                 }
     return total;
 }

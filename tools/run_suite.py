@@ -110,6 +110,15 @@ def main():
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             best = float(t.item()) if best is None else min(best, float(t.item()))
+        per = None
+        if os.environ.get("HQ_SUITE_PER_GROUP"):   # one more execution with every launch timed on its own (no overlap then)
+            c.prepare_state()
+            if world > 1:
+                dist.barrier()
+            _, ms_pg, per_ms = c.execute(per_group=True)
+            per = {"total_ms": round(ms_pg, 3), "launch_ms": [round(x, 3) for x in per_ms],
+                   "launch_backend": [g["backend"][0] for g in groups for _ in range(g["launches"])],
+                   "swap_and_gaps_ms": round(ms_pg - sum(per_ms), 3)}
         norm = torch.tensor([c.norm2()], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(norm)
@@ -133,7 +142,7 @@ def main():
                               "effective_tbps": round(bytes_ / (best * 1e-3) / 1e12, 3),
                               "sweeps_per_s": round(S / (best * 1e-3), 2),
                               "predicted_ms": round(sum(g["predicted_ms"] for g in groups), 2),
-                              "check": verdict, "ok": ok}), flush=True)
+                              "check": verdict, "ok": ok, **({"per_group": per} if per else {})}), flush=True)
         c.close()
     if world > 1:
         dist.barrier()
