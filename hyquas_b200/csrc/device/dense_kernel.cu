@@ -447,7 +447,7 @@ extern "C" int hq_dense_plan_create_ex(int L, uint64_t fixed_mask, uint64_t fixe
     std::memcpy(plan->blob.data(), ufrag.data(), ufrag.size() * 16);
     std::memcpy(plan->blob.data() + plan->o_tab, tables.data(), tables.size() * 2);
     if (rt().ready) {
-        cudaError_t e = cudaMalloc(&plan->dev_blob, plan->blob.size());
+        cudaError_t e = dev_alloc(&plan->dev_blob, plan->blob.size());
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->dev_blob, plan->blob.data(), plan->blob.size(), cudaMemcpyHostToDevice, rt().compute);
         if (e == cudaSuccess) e = cudaStreamSynchronize(rt().compute);
         if (e != cudaSuccess) { delete plan; return cuda_fail(e, "dense plan upload", __FILE__, __LINE__); }
@@ -508,7 +508,7 @@ extern "C" int hq_dense_plan_info(const hq_dense_plan* plan, int* tile_bits, int
 
 extern "C" int hq_dense_plan_destroy(hq_dense_plan* plan) {
     if (!plan) return HQ_OK;
-    if (plan->dev_blob) cudaFree(plan->dev_blob);
+    if (plan->dev_blob) dev_free(plan->dev_blob);
     delete plan;
     return HQ_OK;
 }

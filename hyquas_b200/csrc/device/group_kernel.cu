@@ -84,8 +84,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // The 16 amplitudes of a thread live in named PTX registers (hqa0..hqa31) declared once per kernel; all
 // arithmetic on them is generated inline PTX (group_ops_gen.inc, produced by tools/gen_group_ops.py) that
 // updates them IN PLACE, so the op loop carries no C++-visible state and a gate costs only its FP64 work.
-//   real 2x2 [[a,b],[c,d]] on scalars (u,v):  v <- c*u + d*v ; u <- (det/d)*u + (b/d)*v   (LU form, 4 FP64, no temporary)
-//   the host prepares c, d, det/d, b/d and keeps |d| away from 0 by factoring M = X * (X M) when needed.
+//   real 2x2 [[a,b],[c,d]] on scalars (u,v):  t <- u ; u <- a*u + b*v ; v <- c*t + d*v   (4 FP64 + one register copy)
 }  // namespace hq
 #if HQ_RBITS == 4
 #include "group_ops_gen_r4.inc"
@@ -268,7 +267,7 @@ static bool is_zero(double x) { return x == 0.0; }
 static bool rt_no_butterfly() { static const bool off = getenv("HQ_NO_BUTTERFLY") != nullptr; return off; }
 
 // Pick the arithmetic class from the matrix itself (the type tag is only a hint).
-static bool classify(const hq_gate& g, HostGate& h) {
+static bool classify(const hq_gate& g, HostGate& h, std::complex<double>& launch_scale, bool& any_scale) {
     std::memcpy(h.m, g.mat, sizeof(h.m));
     const double* m = g.mat;
     const bool off0 = is_zero(m[2]) && is_zero(m[3]) && is_zero(m[4]) && is_zero(m[5]);
@@ -278,6 +277,17 @@ static bool classify(const hq_gate& g, HostGate& h) {
         if (g.target < 0) {  // scalar: the reference keeps it in m00 (GCC, kernelOpt.cu:366)
             h.m[6] = h.m[0];
             h.m[7] = h.m[1];
+        }
+        // An uncontrolled diag(d0, d1) = d0 * diag(1, d1/d0): the scalar joins the launch's one deferred factor and what is left
+        // multiplies only the "hi" half -- and can merge into the per-thread / per-register-bit diagonal runs (RZ, the first
+        // factor of a rewritten ZZ rotation, global phases: all free of FP64 work on the "lo" half from here on).
+        if (g.control < 0 && g.control2 < 0 && !(h.m[0] == 1.0 && h.m[1] == 0.0) && std::hypot(h.m[0], h.m[1]) > 0.5) {
+            const std::complex<double> d0(h.m[0], h.m[1]), r = std::complex<double>(h.m[6], h.m[7]) / d0;
+            launch_scale *= d0;
+            any_scale = true;
+            h.m[0] = 1.0; h.m[1] = 0.0;
+            h.m[6] = r.real(); h.m[7] = r.imag();
+            if (std::abs(r - 1.0) < 1e-15) { h.m[6] = 1.0; h.m[7] = 0.0; }   // a pure scalar gate: nothing left to apply
         }
         const bool ident = h.m[0] == 1.0 && h.m[1] == 0.0 && h.m[6] == 1.0 && h.m[7] == 0.0;
         h.kind = OP_DIAG_R;
@@ -309,23 +319,13 @@ static bool classify(const hq_gate& g, HostGate& h) {
     return true;
 }
 
-// Coefficients of the in-place LU update for M = [[a,b],[c,d]]:  {c, d, e = det/d, f = b/d}.
-//   OP_REAL: M real, out = 4 doubles.   OP_RXL: M = [[a, i b'],[i c', d]]; out describes the real matrix
-//   [[a,-b'],[c',d]] (the partner uses -c, -f).   OP_GEN: complex, out = 4 complex numbers.
-static void encode_lu(uint32_t kind, const double* M, double* out) {
+// Coefficients of the 2x2 bodies: OP_REAL {a, b, c, d} = the real matrix; OP_RXL {a, b, c, d} of [[a, i b], [i c, d]];
+// OP_GEN the complex matrix itself (row-major re, im).
+static void encode_2x2(uint32_t kind, const double* M, double* out) {
     std::memset(out, 0, 8 * sizeof(double));
-    if (kind == OP_REAL || kind == OP_RXL) {
-        const double a = M[0], d = M[6];
-        const double b = kind == OP_REAL ? M[2] : -M[3];
-        const double c = kind == OP_REAL ? M[4] : M[5];
-        out[0] = c; out[1] = d; out[2] = (a * d - b * c) / d; out[3] = b / d;
-        return;
-    }
-    typedef std::complex<double> C;
-    const C a(M[0], M[1]), b(M[2], M[3]), c(M[4], M[5]), d(M[6], M[7]);
-    const C e = (a * d - b * c) / d, f = b / d;
-    out[0] = c.real(); out[1] = c.imag(); out[2] = d.real(); out[3] = d.imag();
-    out[4] = e.real(); out[5] = e.imag(); out[6] = f.real(); out[7] = f.imag();
+    if (kind == OP_REAL) { out[0] = M[0]; out[1] = M[2]; out[2] = M[4]; out[3] = M[6]; }
+    else if (kind == OP_RXL) { out[0] = M[0]; out[1] = M[3]; out[2] = M[5]; out[3] = M[6]; }
+    else std::memcpy(out, M, 8 * sizeof(double));
 }
 
 }  // namespace hq
@@ -361,6 +361,8 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         if (tile_mask >> b & 1) phys_to_tile[b] = k++;
 
     // ---- classify + validate ----
+    std::complex<double> launch_scale(1.0, 0.0);   // scalars taken out of gates (diagonals here, butterflies below)
+    bool any_bfly = false;                          // "the launch has a deferred scalar"
     std::vector<HostGate> hg;
     hg.reserve(ngates);
     for (int i = 0; i < ngates; ++i) {
@@ -371,7 +373,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
             HQ_REQUIRE(q < 0 || !(fixed_mask >> q & 1), "gate touches a fixed bit (resolve it when lowering the gate)");
         HostGate h{};
         h.target_phys = g.target; h.c1_phys = g.control; h.c2_phys = g.control2;
-        if (!classify(g, h)) continue;
+        if (!classify(g, h, launch_scale, any_bfly)) continue;
         HQ_REQUIRE(h.diag || phys_to_tile[g.target] >= 0, "non-diagonal gate target is not inside the tile");
         HQ_REQUIRE(g.target < 0 || (g.target != g.control && g.target != g.control2), "control equals target");
         hg.push_back(h);
@@ -454,9 +456,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                 rd.reg.push_back(b);
         std::sort(rd.reg.begin(), rd.reg.end());
     }
-    // butterflies leave their scalars behind: one factor for the whole launch, applied with the last round's diagonal run
-    std::complex<double> launch_scale(1.0, 0.0);
-    bool any_bfly = false;
+    // butterflies leave their scalars behind too: one factor for the whole launch, applied with the last round's diagonal run
     for (const HostGate& h : hg)
         if (h.kind >= OP_BF0 && h.kind <= OP_BF7 && !h.diag) { launch_scale *= std::complex<double>(h.alpha[0], h.alpha[1]); any_bfly = true; }
     const bool trace_plan = getenv("HQ_TRACE_PLAN") != nullptr;
@@ -552,23 +552,9 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                     o.code = op_code(h.kind, tbit, 0);
                     body.push_back(o);
                 } else {
-                    // in-place LU form needs a diagonal entry d that is not small; otherwise apply X*M first and
-                    // then X (a register swap):  M = X * (X*M)
-                    double M[8];
-                    std::memcpy(M, h.m, sizeof(M));
-                    const double dmag = std::hypot(M[6], M[7]);
-                    const bool flip = dmag < 0.35;
-                    if (flip) for (int k = 0; k < 4; ++k) std::swap(M[k], M[4 + k]);   // rows exchanged
-                    const uint32_t kind = (flip && h.kind == OP_RXL) ? (uint32_t)OP_GEN : h.kind;   // X*M leaves the RX-like form
-                    encode_lu(kind, M, o.m);
-                    o.code = op_code(kind, tbit, cb);
+                    encode_2x2(h.kind, h.m, o.m);
+                    o.code = op_code(h.kind, tbit, cb);
                     body.push_back(o);
-                    if (flip) {
-                        DevOp x = o;
-                        std::memset(x.m, 0, sizeof(x.m));
-                        x.code = op_code(OP_SWAP, tbit, cbc);
-                        body.push_back(x);
-                    }
                 }
             }
         }
@@ -736,7 +722,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
     std::memcpy(blob.data() + o_tb, tb.data(), tb.size() * 2);
     plan->o_run = o_run; plan->o_rounds = o_rounds; plan->o_ops = o_ops; plan->o_gt = o_gt; plan->o_tb = o_tb;
     if (rt().ready) {   // without a bound GPU the plan is host-only (partitioner / planner tests)
-        cudaError_t e = cudaMalloc(&plan->dev_blob, total);
+        cudaError_t e = dev_alloc(&plan->dev_blob, total);
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->dev_blob, blob.data(), total, cudaMemcpyHostToDevice, rt().compute);
         if (e == cudaSuccess) e = cudaStreamSynchronize(rt().compute);   // plan creation is off the hot path
         if (e != cudaSuccess) { delete plan; return cuda_fail(e, "plan upload", __FILE__, __LINE__); }
@@ -813,7 +799,7 @@ extern "C" int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes) 
 
 extern "C" int hq_group_plan_destroy(hq_group_plan* plan) {
     if (!plan) return HQ_OK;
-    if (plan->dev_blob) cudaFree(plan->dev_blob);
+    if (plan->dev_blob) dev_free(plan->dev_blob);
     delete plan;
     return HQ_OK;
 }

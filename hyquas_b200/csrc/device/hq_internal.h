@@ -46,6 +46,12 @@ struct Runtime {
 };
 Runtime& rt();
 
+// Small-buffer device allocator for plan tables and scratch (sizes rounded up to a power of two >= 4 KiB; freed buffers are
+// kept on per-size free lists and only go back to the driver at hq_shutdown or above 256 MiB cached).  cudaMalloc/cudaFree
+// synchronise the device and were measured at 2-260 ms per Circuit teardown next to a 16 GiB allocation (tools/e2e_probe.py).
+cudaError_t dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+
 // ---- bit helpers ---------------------------------------------------------------------------------
 inline int popcount64(uint64_t x) { return __builtin_popcountll(x); }
 inline uint64_t pdep64(uint64_t v, uint64_t mask) {

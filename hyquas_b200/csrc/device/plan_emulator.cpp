@@ -59,26 +59,21 @@ int applyOp(Amp* a, const DevOp* op, uint64_t phys) {
         const Amp x = a[lo], y = a[hi];
         const double* m = o.m;
         switch (kind) {
-            case OP_GEN: {   // m = {c, d, e, f} complex: hi <- c*lo + d*hi ; lo <- e*lo + f*hi
-                const std::complex<double> c(m[0], m[1]), d(m[2], m[3]), ee(m[4], m[5]), f(m[6], m[7]);
-                std::complex<double> lo_(x.x, x.y), hi_(y.x, y.y);
-                hi_ = c * lo_ + d * hi_;
-                lo_ = ee * lo_ + f * hi_;
-                a[lo] = {lo_.real(), lo_.imag()}; a[hi] = {hi_.real(), hi_.imag()};
+            case OP_GEN: {   // m = the complex matrix [[a, b], [c, d]]
+                const std::complex<double> A(m[0], m[1]), B(m[2], m[3]), C(m[4], m[5]), D(m[6], m[7]);
+                const std::complex<double> lo_(x.x, x.y), hi_(y.x, y.y);
+                const std::complex<double> nl = A * lo_ + B * hi_, nh = C * lo_ + D * hi_;
+                a[lo] = {nl.real(), nl.imag()}; a[hi] = {nh.real(), nh.imag()};
                 break;
             }
-            case OP_REAL: {  // m = {c, d, e, f} real
-                Amp l = x, h2 = y;
-                h2.x = m[0] * l.x + m[1] * h2.x; l.x = m[2] * l.x + m[3] * h2.x;
-                h2.y = m[0] * l.y + m[1] * h2.y; l.y = m[2] * l.y + m[3] * h2.y;
-                a[lo] = l; a[hi] = h2;
+            case OP_REAL: {  // m = {a, b, c, d}: real [[a, b], [c, d]]
+                a[lo] = {m[0] * x.x + m[1] * y.x, m[0] * x.y + m[1] * y.y};
+                a[hi] = {m[2] * x.x + m[3] * y.x, m[2] * x.y + m[3] * y.y};
                 break;
             }
-            case OP_RXL: {   // (lo.x, hi.y) with {c,d,e,f}; (lo.y, hi.x) with {-c,d,e,-f}
-                Amp l = x, h2 = y;
-                h2.y = m[0] * l.x + m[1] * h2.y; l.x = m[2] * l.x + m[3] * h2.y;
-                h2.x = -m[0] * l.y + m[1] * h2.x; l.y = m[2] * l.y - m[3] * h2.x;
-                a[lo] = l; a[hi] = h2;
+            case OP_RXL: {   // m = {a, b, c, d} of [[a, i b], [i c, d]]
+                a[lo] = {m[0] * x.x - m[1] * y.y, m[0] * x.y + m[1] * y.x};
+                a[hi] = {-m[2] * x.y + m[3] * y.x, m[2] * x.x + m[3] * y.y};
                 break;
             }
             case OP_SWAP: a[lo] = y; a[hi] = x; break;

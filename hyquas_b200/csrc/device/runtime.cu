@@ -103,6 +103,59 @@ extern "C" int hq_init(int device) {
     return HQ_OK;
 }
 
+namespace hq {
+namespace {
+struct SmallPool {
+    std::map<size_t, std::vector<void*>> free_lists;   // rounded size -> cached buffers
+    std::map<void*, size_t> live;                      // handed-out buffer -> rounded size
+    size_t cached_bytes = 0;
+};
+SmallPool& pool() { static SmallPool p; return p; }
+size_t round_size(size_t b) { size_t r = 4096; while (r < b) r <<= 1; return r; }
+}  // namespace
+
+cudaError_t dev_alloc(void** p, size_t bytes) {
+    SmallPool& sp = pool();
+    const size_t r = round_size(bytes);
+    auto it = sp.free_lists.find(r);
+    if (it != sp.free_lists.end() && !it->second.empty()) {
+        *p = it->second.back();
+        it->second.pop_back();
+        sp.cached_bytes -= r;
+    } else {
+        const cudaError_t e = cudaMalloc(p, r);
+        if (e != cudaSuccess) return e;
+    }
+    sp.live[*p] = r;
+    return cudaSuccess;
+}
+
+void dev_free(void* p) {
+    if (!p) return;
+    SmallPool& sp = pool();
+    auto it = sp.live.find(p);
+    if (it == sp.live.end()) { cudaFree(p); return; }
+    const size_t r = it->second;
+    sp.live.erase(it);
+    if (rt().ready && sp.cached_bytes + r <= (size_t(256) << 20)) {
+        // a cached buffer may be handed out again at once: work queued on it must be done (cudaFree would have waited too)
+        cudaStreamSynchronize(rt().compute);
+        sp.free_lists[r].push_back(p);
+        sp.cached_bytes += r;
+    } else {
+        cudaFree(p);
+    }
+}
+
+static void pool_release_all() {
+    SmallPool& sp = pool();
+    for (auto& kv : sp.free_lists)
+        for (void* p : kv.second) cudaFree(p);
+    sp.free_lists.clear();
+    sp.cached_bytes = 0;
+}
+}  // namespace hq
+
 // live state allocations made by hq_state_alloc -> their size (hq_state_free needs it to offer the buffer to the cache)
 static std::map<void*, size_t>& rt_state_sizes() {
     static std::map<void*, size_t> m;
@@ -118,6 +171,7 @@ extern "C" int hq_shutdown(void) {
         rt_state_sizes().erase(r.cached_state);
         cudaFree(r.cached_state);
     }
+    hq::pool_release_all();
     cudaEventDestroy(r.t0);
     cudaEventDestroy(r.t1);
     cudaStreamDestroy(r.compute);
@@ -223,9 +277,9 @@ extern "C" int hq_dump_scan(const void* state, int L, double thresh, int64_t* id
     unsigned long long* d_cnt = nullptr;
     int64_t* d_idx = nullptr;
     double2* d_amp = nullptr;
-    HQ_CUDA(cudaMalloc(&d_cnt, 8));
-    HQ_CUDA(cudaMalloc(&d_idx, (size_t)cap * 8));
-    HQ_CUDA(cudaMalloc(&d_amp, (size_t)cap * 16));
+    HQ_CUDA(dev_alloc(reinterpret_cast<void**>(&d_cnt), 8));
+    HQ_CUDA(dev_alloc(reinterpret_cast<void**>(&d_idx), (size_t)cap * 8));
+    HQ_CUDA(dev_alloc(reinterpret_cast<void**>(&d_amp), (size_t)cap * 16));
     HQ_CUDA(cudaMemsetAsync(d_cnt, 0, 8, rt().compute));
     const int block = 256;
     const int grid = (int)std::min<uint64_t>((n + block - 1) / block, (uint64_t)rt().sm_count * 16);
@@ -242,7 +296,7 @@ extern "C" int hq_dump_scan(const void* state, int L, double thresh, int64_t* id
         HQ_CUDA(cudaMemcpy(hidx.data(), d_idx, (size_t)m * 8, cudaMemcpyDeviceToHost));
         HQ_CUDA(cudaMemcpy(hamp.data(), d_amp, (size_t)m * 16, cudaMemcpyDeviceToHost));
     }
-    cudaFree(d_cnt); cudaFree(d_idx); cudaFree(d_amp);
+    dev_free(d_cnt); dev_free(d_idx); dev_free(d_amp);
     std::vector<int64_t> order(m);
     for (int64_t i = 0; i < m; ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return hidx[a] < hidx[b]; });
@@ -259,7 +313,7 @@ extern "C" int hq_state_norm2(const void* state, int L, double* out) {
     HQ_REQUIRE(rt().ready && state && out, "bad arguments to hq_state_norm2");
     const uint64_t n = 1ull << L;
     double* d = nullptr;
-    HQ_CUDA(cudaMalloc(&d, 8));
+    HQ_CUDA(dev_alloc(reinterpret_cast<void**>(&d), 8));
     HQ_CUDA(cudaMemsetAsync(d, 0, 8, rt().compute));
     const int block = 256;
     const int grid = (int)std::min<uint64_t>((n + block - 1) / block, (uint64_t)rt().sm_count * 8);
@@ -267,7 +321,7 @@ extern "C" int hq_state_norm2(const void* state, int L, double* out) {
     HQ_CUDA(cudaGetLastError());
     HQ_CUDA(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, rt().compute));
     HQ_CUDA(cudaStreamSynchronize(rt().compute));
-    cudaFree(d);
+    dev_free(d);
     return HQ_OK;
 }
 

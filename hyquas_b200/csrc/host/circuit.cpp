@@ -1,4 +1,5 @@
 #include "circuit.h"
+#include "peephole.h"
 
 #include <algorithm>
 #include <cassert>
@@ -31,7 +32,12 @@ void Circuit::compile() {
     auto t0 = chrono::system_clock::now();
     Logger::add("Total Gates %d", int(gates.size()));
     Executor::release(schedule);
-    Compiler compiler(numQubits, gates);
+    hyquas::PeepholeStats ph;
+    const std::vector<Gate> optimised = hyquas::peephole(gates, &ph);
+    if (ph.zzPatterns + ph.hcxhPatterns > 0)
+        Logger::add("Peephole: %d -> %d gates (%d cx-diag-cx, %d h-cx-h patterns made diagonal)", ph.gatesIn, ph.gatesOut, ph.zzPatterns,
+                    ph.hcxhPatterns);
+    Compiler compiler(numQubits, optimised);
     schedule = compiler.run();
     int fullGroups = 0, fullGates = 0, overlapGates = 0;
     for (auto& lg : schedule.localGroups) {

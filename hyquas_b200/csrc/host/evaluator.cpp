@@ -30,7 +30,9 @@ Evaluator::Evaluator() {
     set(GateType::U2, 0.68); set(GateType::U3, 0.68);
     // diag(1,d) gates merge into per-register-bit diagonal runs (one factor per thread)
     set(GateType::T, 0.09); set(GateType::TDG, 0.09); set(GateType::S, 0.09); set(GateType::SDG, 0.09); set(GateType::U1, 0.09);
-    set(GateType::RZ, 0.15); set(GateType::Z, 0.09); set(GateType::X, 0.43); set(GateType::Y, 0.43);
+    // (RZ = scalar * diag(1, e^{ia}): the tile kernel defers the scalar, so it prices like U1)
+    set(GateType::RZ, 0.09); set(GateType::Z, 0.09);
+    set(GateType::GOC, 0.09); set(GateType::ID, 0.0); set(GateType::GII, 0.0); set(GateType::GZZ, 0.0); set(GateType::GCC, 0.0); set(GateType::X, 0.43); set(GateType::Y, 0.43);
     set(GateType::CZ, 0.10); set(GateType::CU1, 0.10); set(GateType::CRZ, 0.25);
     set(GateType::CNOT, 0.25); set(GateType::CY, 0.27); set(GateType::CCX, 0.25);
     set(GateType::CRX, 0.33); set(GateType::CRY, 0.33);

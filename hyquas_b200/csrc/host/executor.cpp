@@ -118,7 +118,7 @@ static std::vector<double> buildDenseMatrix(const DenseBlock& blk, const State& 
         }
         if (bitOf[k.target] < 0) UNREACHABLE()
         const int tb = 1 << bitOf[k.target];
-        #pragma omp parallel for if (K >= 32)
+        #pragma omp parallel for if (K >= 64 && blk.gates.size() >= 64)
         for (int col = 0; col < K; col++) {
             std::complex<double>* v = &U[(size_t)col * K];
             for (int lo = 0; lo < K; lo++) {

@@ -1,0 +1,17 @@
+// Circuit-level peephole pass (see peephole.cpp): gate patterns whose product is diagonal become diagonal gates.
+#pragma once
+#include <vector>
+
+#include "gate.h"
+
+namespace hyquas {
+
+struct PeepholeStats {
+    int gatesIn = 0, gatesOut = 0;
+    int zzPatterns = 0;     // cx a,b ; D b ; cx a,b
+    int hcxhPatterns = 0;   // h t ; cx *,t ... ; h t
+};
+
+std::vector<Gate> peephole(const std::vector<Gate>& gates, PeepholeStats* stats = nullptr);
+
+}  // namespace hyquas

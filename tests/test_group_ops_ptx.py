@@ -79,16 +79,12 @@ def run_ptx(lines, regs, creg, m):
 def matrix_of(kind, m):
     """The 2x2 the planner means by (kind, coefficients m[0..7])."""
     c = lambda i: complex(m[i], m[i + 1])
-    if kind == "GEN":       # LU form {c, d, e, f}: hi' = c lo + d hi ; lo' = e lo + f hi'
-        cc, d, e, f = c(0), c(2), c(4), c(6)
-        return np.array([[e + f * cc, f * d], [cc, d]])
-    if kind == "REAL":
-        cc, d, e, f = m[0], m[1], m[2], m[3]
-        return np.array([[e + f * cc, f * d], [cc, d]], dtype=complex)
-    if kind == "RXL":       # real LU of [[a,-b'],[c',d]] standing for [[a, i b'],[i c', d]]
-        cc, d, e, f = m[0], m[1], m[2], m[3]
-        a, bq = e + f * cc, f * d           # bq = -b'
-        return np.array([[a, -1j * bq], [1j * cc, d]])
+    if kind == "GEN":       # the complex matrix itself
+        return np.array([[c(0), c(2)], [c(4), c(6)]])
+    if kind == "REAL":      # {a, b, c, d} real
+        return np.array([[m[0], m[1]], [m[2], m[3]]], dtype=complex)
+    if kind == "RXL":       # {a, b, c, d} of [[a, i b], [i c, d]]
+        return np.array([[m[0], 1j * m[1]], [1j * m[2], m[3]]])
     if kind == "SWAP":
         return np.array([[0, 1], [1, 0]], dtype=complex)
     if kind == "YL":

@@ -54,10 +54,12 @@ def pairs(tb, R):
     return out
 
 
-def lu2(u, v, c, d, e, f):
-    """v <- c*u + d*v ; u <- e*u + f*v   (in place)"""
-    return [f"mul.f64 {v}, {d}, {v};", f"fma.rn.f64 {v}, {c}, {u}, {v};", f"mul.f64 {u}, {e}, {u};",
-            f"fma.rn.f64 {u}, {f}, {v}, {u};"]
+def lin2(u, v, a, b, c, d, t="hqt"):
+    """(u, v) <- (a*u + b*v, c*u + d*v) on scalars: four FP64 instructions and one register copy.  (An in-place LU form
+    needs no copy but divides by d: gates with a small diagonal -- RX(theta) near pi, a third of random U3 -- then had to run
+    as X * (X M), a complex general op plus a register swap, 2.5x the cost.)"""
+    return [f"mov.f64 {t}, {u};", f"mul.f64 {u}, {a}, {u};", f"fma.rn.f64 {u}, {b}, {v}, {u};", f"mul.f64 {v}, {d}, {v};",
+            f"fma.rn.f64 {v}, {c}, {t}, {v};"]
 
 
 def caxpby(zx, zy, wx, wy, pr, pi, npi, qr, qi, nqi, t="hqt"):
@@ -104,13 +106,14 @@ def bfly_pairs(p, q, lo, hi):
 
 def pair_body(kind, lo, hi):
     """PTX lines for one (lo, hi) pair; coefficients are the statement operands m0..m7 (and negations hqn*)."""
-    if kind == "REAL":      # m = {c, d, e, f}
-        return lu2(re(lo), re(hi), M["m0"], M["m1"], M["m2"], M["m3"]) + lu2(im(lo), im(hi), M["m0"], M["m1"], M["m2"], M["m3"])
-    if kind == "RXL":       # (lo.x, hi.y) with {c,d,e,f}; (lo.y, hi.x) with {-c,d,e,-f}
-        return lu2(re(lo), im(hi), M["m0"], M["m1"], M["m2"], M["m3"]) + lu2(im(lo), re(hi), "hqn0", M["m1"], M["m2"], "hqn3")
-    if kind == "GEN":       # m = {c, d, e, f} complex: hi <- c*lo + d*hi ; lo <- e*lo + f*hi
-        ls = caxpby(re(hi), im(hi), re(lo), im(lo), M["m2"], M["m3"], "hqn3", M["m0"], M["m1"], "hqn1")
-        ls += caxpby(re(lo), im(lo), re(hi), im(hi), M["m4"], M["m5"], "hqn5", M["m6"], M["m7"], "hqn7")
+    if kind == "REAL":      # m = {a, b, c, d}: the real matrix [[a, b], [c, d]] on (lo.x, hi.x) and on (lo.y, hi.y)
+        return lin2(re(lo), re(hi), M["m0"], M["m1"], M["m2"], M["m3"]) + lin2(im(lo), im(hi), M["m0"], M["m1"], M["m2"], M["m3"])
+    if kind == "RXL":       # m = {a, b, c, d} of [[a, i b], [i c, d]]: (lo.x, hi.y) sees [[a, -b], [c, d]], (lo.y, hi.x) sees [[a, b], [-c, d]]
+        return lin2(re(lo), im(hi), M["m0"], "hqn1", M["m2"], M["m3"]) + lin2(im(lo), re(hi), M["m0"], M["m1"], "hqn2", M["m3"])
+    if kind == "GEN":       # m = the complex matrix [[a, b], [c, d]] itself: lo' = a lo + b hi ; hi' = c lo(old) + d hi
+        ls = [f"mov.f64 hqs0, {re(lo)};", f"mov.f64 hqs1, {im(lo)};"]
+        ls += caxpby(re(lo), im(lo), re(hi), im(hi), M["m0"], M["m1"], "hqn1", M["m2"], M["m3"], "hqn3")
+        ls += caxpby(re(hi), im(hi), "hqs0", "hqs1", M["m6"], M["m7"], "hqn7", M["m4"], M["m5"], "hqn5")
         return ls
     if kind == "SWAP":
         ls = []
@@ -136,7 +139,7 @@ def pair_body(kind, lo, hi):
     raise ValueError(kind)
 
 
-NEGS_NEEDED = {"RXL": [0, 3], "GEN": [1, 3, 5, 7], "DIAG_R1": [7], "DIAG_R": [1, 7]}
+NEGS_NEEDED = {"RXL": [1, 2], "GEN": [1, 3, 5, 7], "DIAG_R1": [7], "DIAG_R": [1, 7]}
 # coefficient pairs (m[2j], m[2j+1]) a body reads: one 16-byte shared load each
 COEFF_PAIRS = {"GEN": [0, 1, 2, 3], "REAL": [0, 1], "RXL": [0, 1], "DIAG_R": [0, 3], "DIAG_R1": [3]}
 
@@ -244,7 +247,7 @@ def main():
     print("// one jump, one body: `body` is HQ_OP_BODY_INDEX[code], warp-uniform")
     print("__device__ __forceinline__ void hq_apply_op(uint32_t body, uint32_t creg, uint32_t coeff_addr) {")
     print("    asm volatile(\"{\\n\"")
-    print('        ".reg .f64 hqt, hqu, hqn0, hqn1, hqn3, hqn5, hqn7, hqm<8>;\\n"')
+    print('        ".reg .f64 hqt, hqu, hqs0, hqs1, hqn1, hqn2, hqn3, hqn5, hqn7, hqm<8>;\\n"')
     print('        ".reg .pred hqp;\\n"')
     print('        ".reg .b32 hqx;\\n"')
     labels = ", ".join(f"HQB{i}" for i in range(len(cat)))
