@@ -386,10 +386,14 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         std::vector<int> remaining(hg.size());
         for (size_t i = 0; i < hg.size(); ++i) remaining[i] = (int)i;
         const bool avoid_low_in_round0 = getenv("HQ_ROUND0_LOW_BITS") == nullptr;
-        while (!remaining.empty()) {
-            Round rd;
+        const bool pack_rounds = getenv("HQ_NO_ROUND_PACK") == nullptr;
+        // One pass over the remaining gates: a gate joins the round when nothing it fails to commute with was left behind and,
+        // if it is non-diagonal, its target is (or can still become) one of the round's <= RBITS register qubits.  `allowed`
+        // restricts which tile bits may become register qubits (all ones = first come, first served).
+        auto fill = [&](const std::vector<int>& remaining, uint32_t allowed, bool first_round, Round* out, std::vector<int>* rest) {
             uint64_t blockedX = 0, blockedZ = 0;
-            std::vector<int> rest;
+            std::vector<int> reg;
+            int taken = 0;
             for (int gi : remaining) {
                 const HostGate& h = hg[gi];
                 uint64_t q_nd = 0, q_d = 0;
@@ -402,18 +406,48 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
                     // Round 0 reads the linear TMA image: a register qubit on tile bits 0..2 would put every lane of a
                     // quarter-warp on the same 16-byte bank group (8-way conflicts on all 16 loads; ncu: 3x the ideal
                     // wavefronts over a 4-round launch).  Those gates wait for round 1, which reads the swizzled layout.
-                    if (rounds.empty() && tt < 3 && avoid_low_in_round0) can = false;
-                }
-                if (can && !h.diag) {
-                    const int tt = phys_to_tile[h.target_phys];
-                    if (std::find(rd.reg.begin(), rd.reg.end(), tt) == rd.reg.end()) {
-                        if ((int)rd.reg.size() < RBITS) rd.reg.push_back(tt);
+                    if (first_round && tt < 3 && avoid_low_in_round0) can = false;
+                    if (can && !(allowed >> tt & 1)) can = false;
+                    if (can && std::find(reg.begin(), reg.end(), tt) == reg.end()) {
+                        if ((int)reg.size() < RBITS) reg.push_back(tt);
                         else can = false;
                     }
                 }
-                if (can) rd.gates.push_back(gi);
-                else { blockedX |= q_nd; blockedZ |= q_d; rest.push_back(gi); }
+                if (can) { ++taken; if (out) out->gates.push_back(gi); }
+                else { blockedX |= q_nd; blockedZ |= q_d; if (rest) rest->push_back(gi); }
             }
+            if (out) out->reg = reg;
+            return taken;
+        };
+        while (!remaining.empty()) {
+            const bool first_round = rounds.empty();
+            uint32_t allowed = ~0u;
+            if (pack_rounds) {
+                // Which register qubits?  First come, first served often strands gates behind a qubit that did not make
+                // the cut.  Grow the set one qubit at a time, each time taking the qubit that lets the round hold the most
+                // gates; keep the result when it beats first-come.
+                uint32_t targets = 0;
+                for (int gi : remaining) if (!hg[gi].diag) targets |= 1u << phys_to_tile[hg[gi].target_phys];
+                if (popcount64(targets) > RBITS) {
+                    uint32_t set = 0;
+                    int best_total = fill(remaining, 0u, first_round, nullptr, nullptr);
+                    for (int step = 0; step < RBITS; ++step) {
+                        int best_bit = -1, best_cnt = best_total;
+                        for (int b = 0; b < K; ++b) {
+                            if (!(targets >> b & 1) || (set >> b & 1)) continue;
+                            const int cnt = fill(remaining, set | 1u << b, first_round, nullptr, nullptr);
+                            if (cnt > best_cnt) { best_cnt = cnt; best_bit = b; }
+                        }
+                        if (best_bit < 0) break;
+                        set |= 1u << best_bit;
+                        best_total = best_cnt;
+                    }
+                    if (best_total > fill(remaining, ~0u, first_round, nullptr, nullptr)) allowed = set;
+                }
+            }
+            Round rd;
+            std::vector<int> rest;
+            fill(remaining, allowed, first_round, &rd, &rest);
             rounds.push_back(std::move(rd));
             remaining.swap(rest);
         }

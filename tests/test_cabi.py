@@ -57,3 +57,19 @@ def test_run_without_gpu_fails_loudly():
     assert lib.hq_group_plan_launch(plan, buf, 0) != 0
     assert b"hq_init" in lib.hq_last_error()
     lib.hq_group_plan_destroy(plan)
+
+
+def test_reference_sources_compile_against_our_headers():
+    """main.cpp and micro-benchmark/*.cpp of the reference "must compile unchanged" against this repo's host
+    headers.  Only where the reference tree is mounted (this container); the GPU box runs the resulting binaries instead
+    (tests/test_gpu_parity.py::test_reference_main_on_our_library)."""
+    import os
+    import subprocess
+    import pytest
+    if not os.path.isdir("/root/reference/micro-benchmark"):
+        pytest.skip("reference sources not mounted")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "oracle"), "dropin"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for name in ("main", "local-single", "local-ctr", "two-group-h", "bench-blas"):
+        assert os.path.exists(os.path.join(root, "oracle", "_ref", "dropin_" + name))

@@ -139,6 +139,37 @@ def test_same_dump_as_reference_build(gpu_runtime, tmp_path, name, backend):
     c.close()
 
 
+def _dropin(name):
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "dropin_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("drop-in build not present (oracle/Makefile dropin needs /root/reference)")
+    return exe
+
+
+@pytest.mark.parametrize("name", ["qft_28", "bv_28"])
+def test_reference_main_on_our_library(gpu_runtime, golden_dir, name):
+    """Source-level drop-in: the reference's OWN main.cpp, unmodified, compiled against this repo's host
+    headers and linked with libhyquas_b200.so (oracle/Makefile `dropin`), run on the reference's golden circuits: the
+    amplitude dump it prints must be the golden text."""
+    import re
+    import subprocess
+    exe = _dropin("main")
+    r = subprocess.run([exe, os.path.join(golden_dir, name + ".qasm")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    dump = "".join(l + "\n" for l in r.stdout.splitlines() if re.match(r"^\d+ \d\.\d+: ", l))
+    assert dump == open(os.path.join(golden_dir, name + ".log")).read()
+    assert re.search(r"Logger: Time Cost: \d+ us", r.stdout)
+
+
+def test_reference_microbenchmark_on_our_library(gpu_runtime):
+    """micro-benchmark/two-group-h.cpp of the reference, unmodified, on this library: Circuit / Gate / Logger API used the way
+    the reference's own tools use it."""
+    import subprocess
+    exe = _dropin("two-group-h")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-300:], r.stderr[-500:])
+
+
 @pytest.mark.parametrize("name", ["supremacy_30", "qaoa_30"])
 def test_full_size_round_trip(gpu_runtime, name):
     """BASELINE size (30 qubits, 16 GiB): U^dagger U |0> = |0>, norm preserved -- properties that need no oracle."""
