@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Phase-by-phase wall clock of the public path (QASM text -> parse -> compile -> run -> dump -> close) for supremacy_30, four
+times in one process: shows what the state cache and the small-buffer pool buy (HQ_STATE_CACHE=0 to compare; profiles/
+r01_s22_e2e_probe_nocache.log vs r01_s23_e2e_probe.log)."""
 import time, sys, os
 sys.path.insert(0, "/root/repo")
 from hyquas_b200 import api, circuits as C
