@@ -12,8 +12,9 @@ to 30 + log2(N) qubits (weak scaling: 2^30 amplitudes per GPU).
           Timed with CUDA events on the launching stream over exactly K back-to-back executions on the resident state.
   e2e     same metric through the public API from HOST inputs: QASM text -> parse -> compile (plans uploaded H2D) ->
           run (allocate, |0..0>, execute) -> amplitude dump read back D2H, wall clock per step.
-  roofline      dominant kernel = group_kernel: 32*2^L bytes / mean launch duration (CUDA events per launch) vs
-                MEASURED_PEAKS.json hbm_gbs.
+  roofline      the kernel with the largest share of the step (tile kernel `group_kernel` or fused dense kernel
+                `dense_kernel`): 32*2^L bytes / mean launch duration (CUDA events per launch) vs MEASURED_PEAKS.json
+                hbm_gbs; the live-measured FP64 FMA / DMMA rates are reported next to it (gate-heavy launches are FP64-bound).
   cpu_baseline  the oracle's OpenMP gate-by-gate replay (kind "port") on a bounded sample of the same circuit.
 
 `--impl reference` times the reference's own program (oracle/_ref/hyquas_ref_b*, built from /root/reference by
@@ -294,7 +295,6 @@ def run_ours(args, world, rank, local_rank):
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
            "breakdown_ms": {k: round(v, 2) for k, v in parts.items()},
            "path": "QASM text -> hq_circuit_from_qasm -> compile -> run(alloc, init, execute) -> dump"}
-    api.logger_flush() if False else None
 
     # ---- cpu baseline (rank 0, N=1 only) --------------------------------------------------------------------
     cpu = None
