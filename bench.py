@@ -103,12 +103,17 @@ def cpu_replay(text: str, n: int, budget_s: float = 20.0):
     from oracle import oracle as O
     _, gates = O.parse_qasm(text)
     cores = O.lib().orc_num_threads()
-    while n > 20:
-        try:
-            state = O.zero_state(n)
-            break
-        except MemoryError:
-            n -= 2
+    # Bound the replay's footprint BEFORE touching memory (numpy's zero pages are lazy, so a MemoryError would come too late):
+    # at most 30 qubits (16 GiB) and at most a quarter of what the host has free; the caller scales by 2^(n - n_used).
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    n = min(n, 30)
+    while n > 20 and (16 << n) > avail // 4:
+        n -= 1
+    state = O.zero_state(n)
     # spread the state so every gate does real work, then time a sample
     O.apply(state, n, [O.OGate("h", q) for q in range(min(n, 3))])
     per_gate_guess = (1 << n) * 16 * 2 / 8e9
@@ -124,6 +129,8 @@ def run_reference(args, world, rank):
     """Reference arm: the reference's own binary on the same circuit (GPU), else the oracle replay (host cores)."""
     if rank != 0:
         return
+    if world > 1:   # torchrun pins OMP_NUM_THREADS=1 per rank; only rank 0 works here, so it may use every host core
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     name, n, text = workload(args, world)
     peak, _ = measured_peaks()
     sweeps = int(os.environ.get("HQ_BENCH_SWEEPS", "0"))
