@@ -29,6 +29,12 @@ void Circuit::destroyState() {
 }
 
 void Circuit::compile() {
+    if (numQubits - MyGlobalVars::bit < 9) {
+        // the kernels work on tiles of >= 2^9 amplitudes per GPU (the reference's tile is LOCAL_QUBIT_SIZE = 10 qubits, utils.h:45)
+        printf("hyquas_b200: %d qubits on %d GPU(s) leaves %d local qubits; at least 9 are needed\n", numQubits, MyGlobalVars::numGPUs,
+               numQubits - MyGlobalVars::bit);
+        exit(1);
+    }
     auto t0 = chrono::system_clock::now();
     Logger::add("Total Gates %d", int(gates.size()));
     Executor::release(schedule);
