@@ -9,42 +9,44 @@
 #include "gate.h"
 #include "schedule.h"
 
-struct ResultItem {
-    ResultItem() = default;
-    ResultItem(const qindex& idx, const qComplex& amp): idx(idx), amp(amp) {}
+struct ResultItem {   // one line of the amplitude dump: logical index + amplitude
     qindex idx;
     qComplex amp;
+    ResultItem() = default;
+    ResultItem(const qindex& i, const qComplex& a): idx(i), amp(a) {}
     std::string str() const;
     void print() { fputs(str().c_str(), stdout); }
-    bool operator < (const ResultItem& b) const { return idx < b.idx; }
+    bool operator < (const ResultItem& o) const { return idx < o.idx; }
 };
 
 class Circuit {
 public:
-    Circuit(int numQubits): numQubits(numQubits) {}
+    const int numQubits;
+    Circuit(int n): numQubits(n) {}
     ~Circuit();
-    void compile();
-    int run(bool copy_back = true, bool destroy = true);
-    void addGate(const Gate& gate) { gates.push_back(gate); }
-    void dumpGates();
+
+    // ---- the reference's surface --------------------------------------------------------------------------
+    void addGate(const Gate& g) { gates.push_back(g); }
+    void compile();                                          // peephole -> partition -> device plans
+    int run(bool copy_back = true, bool destroy = true);     // -> microseconds of the execution phase
     void printState();
+    void dumpGates();
     ResultItem ampAt(qindex idx);
     qComplex ampAtGPU(qindex idx);
-    const int numQubits;
 
-    // extras used by the C-ABI / tests / bench
-    std::string stateDump();                          // the text printState() prints
+    // ---- extras used by the C-ABI / tests / bench -----------------------------------------------------------
+    void prepareState();                                     // (re)allocate + |0..0>
+    int execute(std::vector<float>* perGroupMs = nullptr);   // the timed part of run() on the resident state
+    void destroyState();
+    std::string stateDump();                                 // the text printState() prints
+    bool fullState(std::vector<qComplex>& out);              // all 2^n amplitudes in LOGICAL order (single process, small n)
+    bool localShard(double* out);                            // this process' amplitudes in PHYSICAL order
+    double norm2();                                          // sum |a|^2 over this process' shard
+    size_t planBytes() const;                                // bytes of device tables uploaded by compile()
+    size_t dumpBytes() const { return dumpItems.size() * sizeof(ResultItem); }
     const Schedule& getSchedule() const { return schedule; }
     const std::vector<Gate>& getGates() const { return gates; }
-    bool fullState(std::vector<qComplex>& out);       // all 2^n amplitudes in LOGICAL order (single process, small n)
-    bool localShard(double* out);                     // this process' amplitudes in PHYSICAL order
-    double lastDeviceMs = 0;                          // CUDA-event time of the last run()
-    void prepareState();                              // (re)allocate + |0..0>
-    int execute(std::vector<float>* perGroupMs = nullptr);   // the timed part of run() on the resident state
-    double norm2();                                   // sum |a|^2 over this process' shard
-    size_t planBytes() const;                         // bytes of device tables uploaded by compile()
-    size_t dumpBytes() const { return dumpItems.size() * sizeof(ResultItem); }
-    void destroyState();
+    double lastDeviceMs = 0;                                 // CUDA-event time of the last run()
 
 private:
     qindex toPhysicalID(qindex idx);
@@ -53,7 +55,7 @@ private:
     std::vector<Gate> gates;
     std::vector<qComplex*> deviceStateVec;
     Schedule schedule;
-    std::vector<qComplex> result;                     // host copy in PHYSICAL order (copy_back)
-    std::vector<ResultItem> dumpItems;                // what printState() shows, captured before destroy
+    std::vector<qComplex> result;                            // host copy in PHYSICAL order (copy_back)
+    std::vector<ResultItem> dumpItems;                       // what printState() shows, captured before destroy
     bool compiled = false;
 };

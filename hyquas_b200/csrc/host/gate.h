@@ -16,49 +16,34 @@ struct Gate {
     GateType type;
     qComplex mat[2][2];
     std::string name;
-    int targetQubit;
-    int controlQubit;   // -1 if no control
-    int controlQubit2;  // -1 if no second control
+    int targetQubit, controlQubit, controlQubit2;   // controls: -1 when absent
     Gate(): gateID(0), type(GateType::ID), targetQubit(-1), controlQubit(-1), controlQubit2(-1) {}
+
     bool isControlGate() const { return controlQubit != -1; }
     bool isC2Gate() const { return controlQubit2 != -1; }
-    // true when the matrix is diagonal (decided from the matrix, so TDG/ID/GOC... are covered too)
-    bool isDiagonal() const {
-        return mat[0][1].x == 0 && mat[0][1].y == 0 && mat[1][0].x == 0 && mat[1][0].y == 0;
-    }
-    static Gate CCX(int c1, int c2, int targetQubit);
-    static Gate CNOT(int controlQubit, int targetQubit);
-    static Gate CY(int controlQubit, int targetQubit);
-    static Gate CZ(int controlQubit, int targetQubit);
-    static Gate CRX(int controlQubit, int targetQubit, qreal angle);
-    static Gate CRY(int controlQubit, int targetQubit, qreal angle);
-    static Gate CU1(int controlQubit, int targetQubit, qreal lambda);
-    static Gate CRZ(int controlQubit, int targetQubit, qreal angle);
-    static Gate U1(int targetQubit, qreal lambda);
-    static Gate U2(int targetQubit, qreal phi, qreal lambda);
-    static Gate U3(int targetQubit, qreal theta, qreal phi, qreal lambda);
-    static Gate H(int targetQubit);
-    static Gate X(int targetQubit);
-    static Gate Y(int targetQubit);
-    static Gate Z(int targetQubit);
-    static Gate S(int targetQubit);
-    static Gate SDG(int targetQubit);
-    static Gate T(int targetQubit);
-    static Gate TDG(int targetQubit);
-    static Gate RX(int targetQubit, qreal angle);
-    static Gate RY(int targetQubit, qreal angle);
-    static Gate RZ(int targetQubit, qreal angle);
-    static Gate ID(int targetQubit);
-    static Gate GII(int targetQubit);
-    static Gate GZZ(int targetQubit);
-    static Gate GOC(int targetQubit, qreal real, qreal imag);
-    static Gate GCC(int targetQubit, qreal real, qreal imag);
-    static Gate random(int lo, int hi);
+    // decided from the matrix (so TDG / ID / GOC ... are covered, whatever their type tag says)
+    bool isDiagonal() const { return mat[0][1].x == 0 && mat[0][1].y == 0 && mat[1][0].x == 0 && mat[1][0].y == 0; }
+
+    // factories, by shape: (controls..., target[, angles...]) -- same names and argument order as the reference's
+    static Gate CCX(int c1, int c2, int t);
+    static Gate CNOT(int c, int t);          static Gate CY(int c, int t);             static Gate CZ(int c, int t);
+    static Gate CRX(int c, int t, qreal a);  static Gate CRY(int c, int t, qreal a);   static Gate CRZ(int c, int t, qreal a);
+    static Gate CU1(int c, int t, qreal lambda);
+    static Gate U1(int t, qreal lambda);     static Gate U2(int t, qreal phi, qreal lambda);
+    static Gate U3(int t, qreal theta, qreal phi, qreal lambda);
+    static Gate H(int t);    static Gate X(int t);    static Gate Y(int t);    static Gate Z(int t);
+    static Gate S(int t);    static Gate SDG(int t);  static Gate T(int t);    static Gate TDG(int t);
+    static Gate RX(int t, qreal a);          static Gate RY(int t, qreal a);           static Gate RZ(int t, qreal a);
+    // internal gates produced by per-GPU lowering: identity, i*I, -I, diag(1, z), z*I
+    static Gate ID(int t);   static Gate GII(int t);  static Gate GZZ(int t);
+    static Gate GOC(int t, qreal re, qreal im);       static Gate GCC(int t, qreal re, qreal im);
+
+    static Gate random(int lo, int hi);                 // micro-benchmarks: random type / angles on a qubit in [lo, hi)
     static Gate random(int lo, int hi, GateType type);
-    static Gate control(int controlQubit, int targetQubit, GateType type);
-    static GateType toCU(GateType type);
+    static Gate control(int c, int t, GateType type);   // controlled gate of a given type with random angles
+    static GateType toCU(GateType type);                // U -> its controlled form, and back
     static GateType toU(GateType type);
     static std::string get_name(GateType ty);
-    // generic constructor used by the factories and by the QASM front end
+    // generic constructor used by the factories, the QASM front end and the peephole pass
     static Gate make(GateType type, const char* name, int c2, int c1, int t, const qComplex m[4]);
 };
