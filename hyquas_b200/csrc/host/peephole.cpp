@@ -11,6 +11,13 @@
 //   P2  h t ; cx c1,t ; ... ; cx ck,t ; h t     with nothing else touching t in between
 //       = cz c1,t ; ... ; cz ck,t                (H X H = Z; the phase-kickback core of Bernstein-Vazirani)
 //
+//   P3  (opt-in, HQ_PEEPHOLE_X=1)  x a ; G1 ; ... ; Gk ; x a    where every gate in between that touches a is diagonal (k >= 1)
+//       = G1' ... Gk' with the roles of a = 0 and a = 1 exchanged in each Gi (the oracle-with-shift core of hidden-shift
+//       circuits: x q ; cz q,r ; x q  =  z r ; cz q,r).  Each Gi' is emitted in diag(1, .) form:
+//         diag(d0,d1) on a                  ->  diag(d1, d0)  =  (scalar d1) diag(1, d0/d1)
+//         controlled-diag(d0,d1), target a  ->  diag(1, d1) on the control ; controlled-diag(1, d0/d1)
+//         controlled-diag(d0,d1), control a ->  diag(d0, d1) on the target ; controlled-diag(1/d0, 1/d1)
+//
 // HQ_PEEPHOLE=0 switches the pass off.
 #include "peephole.h"
 
@@ -120,6 +127,63 @@ std::vector<Gate> peephole(const std::vector<Gate>& in, PeepholeStats* stats) {
     }
 
     rebuild();
+
+    // P3: x a ; (gates, those touching a all diagonal with at most one control) ; x a.  Opt-in (HQ_PEEPHOLE_X=1): it removes
+    // every x of a hidden-shift circuit, but the z gates it leaves behind changed the greedy cut of hidden_shift_28 from 4 to 5
+    // sweeps (predicted 9.9 -> 10.2 ms), and no GPU time was left to measure it.
+    const bool xPass = getenv("HQ_PEEPHOLE_X") != nullptr && atoi(getenv("HQ_PEEPHOLE_X")) != 0;
+    for (int sweep = 0; sweep < 64 && xPass; sweep++) {
+        qindex dirty = 0;
+        int found = 0;
+        auto isX = [](const Gate& q) { return q.type == GateType::X && q.controlQubit == -1 && q.controlQubit2 == -1; };
+        for (size_t i = 0; i < g.size(); i++) {
+            if (dead[i] || !replacement[i].empty() || !isX(g[i])) continue;
+            const int a = g[i].targetQubit;
+            if (dirty >> a & 1) continue;
+            std::vector<int> mid;
+            int j = (int)i, close = -1;
+            bool clean = true;
+            while ((j = nextTouching(g, dead, (size_t)j, a, -1)) >= 0) {
+                if (!replacement[j].empty()) break;
+                if (isX(g[j])) { close = j; break; }
+                if (!g[j].isDiagonal() || g[j].controlQubit2 != -1) break;
+                const int other = g[j].controlQubit == a ? g[j].targetQubit : g[j].controlQubit;
+                if (other >= 0 && (dirty >> other & 1)) { clean = false; break; }
+                mid.push_back(j);
+            }
+            if (close < 0 || mid.empty() || !clean || mid.size() > 8) continue;
+            bool ok = true;
+            for (int m : mid) {
+                const Cx d0(g[m].mat[0][0].x, g[m].mat[0][0].y), d1(g[m].mat[1][1].x, g[m].mat[1][1].y);
+                if (std::abs(d0) < 0.5 || std::abs(d1) < 0.5) ok = false;
+            }
+            if (!ok) continue;
+            for (int m : mid) {
+                const Gate& G = g[m];
+                const Cx d0(G.mat[0][0].x, G.mat[0][0].y), d1(G.mat[1][1].x, G.mat[1][1].y), one(1, 0);
+                if (G.controlQubit == -1) {                 // diag(d0,d1) on a -> diag(d1,d0)
+                    replacement[m].push_back(diagGate(GateType::RZ, "RZ", -1, a, d1, d0));
+                } else if (G.targetQubit == a) {            // acts when control = 1: entries exchanged
+                    const int c = G.controlQubit;
+                    replacement[m].push_back(diagGate(GateType::U1, "U1", -1, c, one, d1));
+                    replacement[m].push_back(diagGate(GateType::CU1, "CU1", c, a, one, d0 / d1));
+                    dirty |= qindex(1) << c;
+                } else {                                    // a is the control: now acts when a = 0
+                    const int t = G.targetQubit;
+                    replacement[m].push_back(diagGate(GateType::RZ, "RZ", -1, t, d0, d1));
+                    replacement[m].push_back(diagGate(GateType::CRZ, "CRZ", a, t, one / d0, one / d1));
+                    dirty |= qindex(1) << t;
+                }
+            }
+            dead[i] = dead[close] = 1;
+            dirty |= qindex(1) << a;
+            found++;
+        }
+        st.xdxPatterns += found;
+        if (!found) break;
+        rebuild();
+    }
+
     st.gatesOut = (int)g.size();
     if (stats) *stats = st;
     return g;

@@ -10,6 +10,7 @@ struct PeepholeStats {
     int gatesIn = 0, gatesOut = 0;
     int zzPatterns = 0;     // cx a,b ; D b ; cx a,b
     int hcxhPatterns = 0;   // h t ; cx *,t ... ; h t
+    int xdxPatterns = 0;    // x a ; diagonal gates ; x a
 };
 
 std::vector<Gate> peephole(const std::vector<Gate>& gates, PeepholeStats* stats = nullptr);

@@ -68,6 +68,34 @@ def test_h_cx_h_blocked_by_other_gate_on_target():
     assert info["gates"] == ngates
 
 
+def test_x_diag_x_becomes_diagonal(monkeypatch):
+    """x a ; diagonal gates touching a (as target, as control, uncontrolled) ; x a  ->  no x left (opt-in pass)."""
+    monkeypatch.setenv("HQ_PEEPHOLE_X", "1")
+    body = ["x q[3];", "cz q[3],q[5];", "h q[8];", "cu1(0.7) q[6],q[3];", "rz(0.9) q[3];", "t q[3];", "crz(1.1) q[3],q[7];", "x q[3];",
+            "x q[9];", "cz q[0],q[9];", "x q[9];"]
+    got, want, info, ngates = run(qasm(10, PREP + body + ["h q[3];", "h q[5];", "rx(0.2) q[9];"]))
+    assert np.max(np.abs(got - want)) < 1e-12
+    api.logger_flush()
+
+
+def test_x_diag_x_blocked_by_non_diagonal(monkeypatch):
+    monkeypatch.setenv("HQ_PEEPHOLE_X", "1")
+    body = ["x q[3];", "cz q[3],q[5];", "cx q[3],q[4];", "x q[3];",        # cx with control 3 is not diagonal: must stay
+            "x q[6];", "h q[6];", "x q[6];"]
+    got, want, info, ngates = run(qasm(10, PREP + body))
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert info["gates"] == ngates
+
+
+def test_hidden_shift_loses_its_x_gates(monkeypatch):
+    monkeypatch.setenv("HQ_PEEPHOLE_X", "1")
+    text = C.generate("hidden_shift_14")
+    got, want, info, ngates = run(text)
+    assert np.max(np.abs(got - want)) < 1e-12
+    nx = sum(1 for l in text.splitlines() if l.startswith("x "))
+    assert nx > 0 and info["gates"] <= ngates       # every x pair is gone; each cz in between became z + cz
+
+
 def test_switch_off(monkeypatch):
     text = C.generate("qaoa_12")
     monkeypatch.setenv("HQ_PEEPHOLE", "0")
@@ -78,8 +106,9 @@ def test_switch_off(monkeypatch):
     assert info1["groups"] <= info0["groups"]
 
 
-@pytest.mark.parametrize("seed", range(40))
-def test_random_pattern_rich_circuits(seed):
+@pytest.mark.parametrize("seed", range(80))
+def test_random_pattern_rich_circuits(seed, monkeypatch):
+    monkeypatch.setenv("HQ_PEEPHOLE_X", str(seed % 2))      # odd seeds also run the opt-in x-diag-x pass
     """Gate soup over 6 qubits drawn from exactly the alphabet the patterns are made of, so matches, near misses and nested
     cases all occur; every circuit is checked against the oracle."""
     rng = random.Random(seed)
@@ -87,7 +116,8 @@ def test_random_pattern_rich_circuits(seed):
     lines = list(PREP)
     def soup():
         q = rng.randrange(6)
-        return rng.choice([f"t q[{q}];", f"h q[{q}];", f"rz(0.7) q[{q}];", f"cx q[{q}],q[{(q + 1 + rng.randrange(5)) % 6}];"])
+        return rng.choice([f"t q[{q}];", f"h q[{q}];", f"rz(0.7) q[{q}];", f"cx q[{q}],q[{(q + 1 + rng.randrange(5)) % 6}];", f"x q[{q}];",
+                           f"cz q[{q}],q[{(q + 1 + rng.randrange(5)) % 6}];"])
 
     for _ in range(70):
         k = rng.random()
@@ -98,7 +128,12 @@ def test_random_pattern_rich_circuits(seed):
         elif k < 0.25:
             mid = [soup()] if rng.random() < 0.5 else []
             lines += [f"h q[{b}];", f"cx q[{a}],q[{b}];"] + mid + [f"cx q[{(a + 1) % 6 if (a + 1) % 6 != b else (a + 2) % 6}],q[{b}];", f"h q[{b}];"]
-        elif k < 0.40:
+        elif k < 0.33:   # x ... x sandwiches around diagonal (or, as a near miss, other) gates
+            lines += [f"x q[{a}];", rng.choice([f"cz q[{a}],q[{b}];", f"cu1(0.4) q[{b}],q[{a}];", f"rz(1.3) q[{a}];", soup()])]
+            if rng.random() < 0.5:
+                lines.append(soup())
+            lines.append(f"x q[{a}];")
+        elif k < 0.45:
             lines.append(f"cx q[{a}],q[{b}];")
         elif k < 0.60:
             lines.append(f"rz({rng.uniform(0.1, 3.0):.6f}) q[{a}];")
