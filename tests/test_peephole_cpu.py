@@ -73,9 +73,12 @@ def test_x_diag_x_becomes_diagonal(monkeypatch):
     monkeypatch.setenv("HQ_PEEPHOLE_X", "1")
     body = ["x q[3];", "cz q[3],q[5];", "h q[8];", "cu1(0.7) q[6],q[3];", "rz(0.9) q[3];", "t q[3];", "crz(1.1) q[3],q[7];", "x q[3];",
             "x q[9];", "cz q[0],q[9];", "x q[9];"]
+    api.logger_flush()
     got, want, info, ngates = run(qasm(10, PREP + body + ["h q[3];", "h q[5];", "rx(0.2) q[9];"]))
     assert np.max(np.abs(got - want)) < 1e-12
-    api.logger_flush()
+    import re
+    m = re.search(r"(\d+) x-diag-x patterns", api.logger_flush())
+    assert m and int(m.group(1)) == 2
 
 
 def test_x_diag_x_blocked_by_non_diagonal(monkeypatch):
