@@ -59,6 +59,9 @@ _SIGS = {
     "hq_group_plan_table_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_local_exchanges": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
+    "hq_group_plans_warm": (_c.c_int, [_P(_c.c_void_p), _c.c_int]),
+    "hq_group_plan_is_specialised": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
+    "hq_jit_stats": (_c.c_int, [_P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_double)]),
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
     "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),
     "hq_microbench_copy": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
@@ -113,6 +116,8 @@ _SIGS = {
     "hq_circuit_destroy": (_c.c_int, [_c.c_void_p]),
     # test hook (device/plan_emulator.cpp) -- used by the CPU test-suite only
     "hq_debug_group_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_debug_group_plan_jit_source": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_char_p, _c.c_size_t, _P(_c.c_size_t)]),
+    "hq_debug_jit_compile_to_file": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_size_t]),
     "hq_debug_dense_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "hq_debug_num_stages": (_c.c_int, [_c.c_void_p]),
     "hq_debug_stage_swap": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int),

@@ -1,0 +1,31 @@
+// Per-group specialised gate-group kernels: source emitter (group_jit.cpp) and NVRTC runtime + cache (group_jit_rt.cpp).
+#pragma once
+#include <cstddef>
+#include <string>
+
+struct hq_group_plan;
+
+namespace hq {
+
+// CUDA C++ source of the kernel `hq_group_jit(double2* state)` that applies exactly this plan (host = false), or of the
+// serial C++ function `hq_group_jit_host(double* state)` with the same arithmetic text (host = true; CPU tests only).
+// Empty string: the emitter does not handle this plan (the interpreter kernel does).
+std::string jit_emit_source(const hq_group_plan& plan, bool host);
+int jit_min_blocks(int K);
+const char* jit_device_prologue();
+const char* jit_device_epilogue();
+const char* jit_host_prologue();
+const char* jit_host_epilogue();
+
+struct JitKernel;   // one loaded cubin
+// Compile (or fetch from the in-memory / on-disk cache) and load.  Returns nullptr and sets `why` when NVRTC or the driver
+// entry points are unavailable or the compile fails; the caller then keeps the interpreter kernel.
+JitKernel* jit_get(const std::string& source, size_t dynamic_smem, std::string* why);
+// Compile a batch of sources on all host cores (cold cache), without loading; a later jit_get() finds them cached.
+void jit_precompile(const std::string* sources, int n);
+int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state);
+int jit_max_blocks_per_sm(JitKernel* k, int block, size_t smem);
+void jit_stats(int* kernels, int* compiled, int* disk_hits, double* compile_seconds);
+bool jit_enabled();
+
+}  // namespace hq

@@ -35,6 +35,7 @@
 
 #include "hq_internal.h"
 #include "group_plan.h"
+#include "group_jit.h"
 
 namespace hq {
 
@@ -500,6 +501,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
     std::vector<DevOp> dops;
     std::vector<uint16_t> tb((size_t)nrounds * 2 * NT);
     std::vector<uint64_t> gt((size_t)nrounds * NT);
+    std::vector<hq_group_plan::RoundMeta> meta(nrounds);
     for (int r = 0; r < nrounds; ++r) {
         const Round& rd = rounds[r];
         int reg_of_tile[16];
@@ -623,6 +625,8 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         }
         if (allow_local) tbits.insert(tbits.end(), warp_bits[r].begin(), warp_bits[r].end());
 
+        meta[r].tbits = tbits;
+        for (int b = 0; b < RBITS; ++b) meta[r].reg[b] = rd.reg[b];
         DevRound& d = drounds[r];
         std::memset(&d, 0, sizeof(d));
         for (int i = 0; i < R; ++i) {
@@ -711,6 +715,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
 
     auto* plan = new hq_group_plan();
     plan->L = L; plan->K = K; plan->NT = NT; plan->tile_mask = tile_mask;
+    plan->meta = std::move(meta); plan->fixed_mask = fixed_mask; plan->fixed_value = fixed_value;
     plan->nrounds = nrounds; plan->nops = (int)dops.size(); plan->ngates = (int)hg.size(); plan->nlocal = nlocal;
     GroupParams& p = plan->p;
     p.ntiles = 1ull << (L - K - popcount64(fixed_mask));
@@ -767,7 +772,42 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         p.gt = reinterpret_cast<const uint64_t*>(d + o_gt);
         p.tb = reinterpret_cast<const uint16_t*>(d + o_tb);
     }
+    // the specialised kernel's source (compiled at the first launch, or for a whole schedule at once by hq_group_plans_warm)
+    if (rt().ready && jit_enabled()) plan->jit_source = jit_emit_source(*plan, false);
     *out = plan;
+    return HQ_OK;
+}
+
+// Resolve the specialised kernel of a plan: memory cache, disk cache, or an NVRTC compile.
+static void resolve_jit(const hq_group_plan* plan) {
+    if (plan->jit || plan->jit_failed || plan->jit_source.empty()) return;
+    std::string why;
+    const size_t smem = (size_t)(16u << plan->K) + 16;
+    JitKernel* k = jit_get(plan->jit_source, smem, &why);
+    if (!k) {
+        plan->jit_failed = true;
+        static bool warned = false;
+        if (!warned) { fprintf(stderr, "[hyquas_b200] specialised gate-group kernels unavailable (%s); using the interpreter kernel\n", why.c_str()); warned = true; }
+        return;
+    }
+    plan->jit = k;
+    plan->jit_occupancy = jit_max_blocks_per_sm(k, plan->NT, smem);
+}
+
+extern "C" int hq_group_plans_warm(hq_group_plan* const* plans, int n) {
+    HQ_REQUIRE(n >= 0 && (n == 0 || plans != nullptr), "bad plan list");
+    if (!rt().ready || !jit_enabled()) return HQ_OK;
+    std::vector<std::string> src;
+    for (int i = 0; i < n; ++i)
+        if (plans[i] && !plans[i]->jit && !plans[i]->jit_failed && !plans[i]->jit_source.empty()) src.push_back(plans[i]->jit_source);
+    jit_precompile(src.data(), (int)src.size());
+    for (int i = 0; i < n; ++i) if (plans[i]) resolve_jit(plans[i]);
+    return HQ_OK;
+}
+
+extern "C" int hq_group_plan_is_specialised(const hq_group_plan* plan, int* yes) {
+    HQ_REQUIRE(plan != nullptr && yes != nullptr, "null argument");
+    *yes = plan->jit != nullptr;
     return HQ_OK;
 }
 
@@ -799,6 +839,11 @@ extern "C" int hq_group_plan_launch(const hq_group_plan* plan, void* state, int 
     GroupParams p = plan->p;
     p.state = static_cast<double2*>(state);
     cudaStream_t s = on_comm_stream ? rt().comm : rt().compute;
+    resolve_jit(plan);
+    if (plan->jit) {
+        plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * plan->jit_occupancy - rt().reserved_ctas));
+        return jit_launch(static_cast<JitKernel*>(plan->jit), plan->grid, plan->NT, (size_t)(16u << plan->K) + 16, s, state);
+    }
     const bool relaxed = rt().relaxed_regs;   // fewer resident CTAs, no register cap (HQ_RELAXED_REGS=1)
     // resident CTAs per SM asked of ptxas: 2048 threads' worth of registers at 64 (RBITS=3) / 128 (RBITS=4) per thread
     constexpr int B12 = RBITS == 4 ? 2 : 2, B11 = 2 * B12, B10 = 4 * B12;

@@ -2,6 +2,7 @@
 // test-only plan emulator (plan_emulator.cpp).
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 #include <vector_types.h>
 
@@ -97,4 +98,13 @@ struct hq_group_plan {
     size_t o_run = 0, o_rounds = 0, o_ops = 0, o_gt = 0, o_tb = 0;
     void* dev_blob = nullptr;             // uploaded at creation when a GPU is bound
     hq::GroupParams p{};                  // pointers refer to dev_blob
+    // what the JIT emitter (group_jit.cpp) needs beyond the tables: per round the register qubits and the thread-id-bit ->
+    // tile-bit map the tables were built from, and the launch geometry
+    struct RoundMeta { int reg[hq::RBITS]; std::vector<int> tbits; };
+    std::vector<RoundMeta> meta;
+    uint64_t fixed_mask = 0, fixed_value = 0;
+    std::string jit_source;               // CUDA source of this plan's specialised kernel (empty: interpreter kernel only)
+    mutable void* jit = nullptr;          // hq::JitKernel*, resolved at the first launch (or by hq_group_plans_warm)
+    mutable bool jit_failed = false;
+    mutable int jit_occupancy = 0;
 };

@@ -177,6 +177,15 @@ void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
         for (auto& gg : lg.overlapGroups) prepareGroup(gg, numQubits, lg.swap.localBit);
         for (auto& gg : lg.fullGroups) prepareGroup(gg, numQubits, {});
     }
+    if (hostOnly) return;
+    // tile-kernel groups run as per-group specialised kernels: fetch them from the cache, compiling the misses on all cores
+    std::vector<hq_group_plan*> tilePlans;
+    for (auto& lg : schedule.localGroups)
+        for (auto* groups : {&lg.overlapGroups, &lg.fullGroups})
+            for (auto& gg : *groups)
+                if (gg.backend != Backend::BLAS)
+                    for (void* p : gg.plans) tilePlans.push_back(static_cast<hq_group_plan*>(p));
+    checkHq(hq_group_plans_warm(tilePlans.data(), (int)tilePlans.size()));
 }
 
 void Executor::release(Schedule& schedule) {

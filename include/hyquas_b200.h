@@ -88,6 +88,12 @@ int hq_group_plan_info(const hq_group_plan* plan, int* rounds, int* ops, int* gr
 int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes);   /* size of the uploaded device tables */
 int hq_group_plan_local_exchanges(const hq_group_plan* plan, int* n);   /* round exchanges done with a warp-level barrier */
 int hq_group_plan_destroy(hq_group_plan* plan);
+/* Gate groups run as per-group specialised kernels (NVRTC, sm_100a; cached in memory and under $HQ_JIT_CACHE or
+ * ~/.cache/hyquas_b200/jit; HQ_JIT=0 keeps the interpreter kernel).  A plan compiles at its first launch; warming a whole
+ * schedule's plans at once compiles the cache misses on all host cores. */
+int hq_group_plans_warm(hq_group_plan* const* plans, int n);
+int hq_group_plan_is_specialised(const hq_group_plan* plan, int* yes);
+int hq_jit_stats(int* kernels_loaded, int* compiled, int* disk_hits, double* compile_seconds);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 
 /* ---- fused dense-matrix kernel (replaces the TransMM path: cuttExecute + cublasZgemm in Executor::applyBlasGroup,

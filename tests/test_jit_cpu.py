@@ -1,0 +1,125 @@
+"""The per-group kernel specialiser (device/group_jit.cpp) on CPU: the emitter's HOST flavour -- same arithmetic text as the
+CUDA source, threads and tiles replayed serially -- is compiled with g++ and compared with the oracle; the CUDA flavour is
+compiled by NVRTC for sm_100a (no GPU needed) to prove it is valid source that fits the register budget."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from hyquas_b200 import circuits as C
+from hyquas_b200._lib import check, lib
+from oracle import oracle as O
+from hyquas_b200._lib import HqGate
+
+
+def pack(gates):
+    arr = (HqGate * max(1, len(gates)))()
+    for i, g in enumerate(gates):
+        arr[i].type, arr[i].target, arr[i].control, arr[i].control2 = 0, g.target, g.control, g.control2
+        m = np.asarray(g.mat).reshape(4)
+        for j in range(4):
+            arr[i].mat[2 * j], arr[i].mat[2 * j + 1] = m[j].real, m[j].imag
+    return arr
+
+
+def random_state(n, seed):
+    r = np.random.default_rng(seed)
+    s = (r.standard_normal(1 << n) + 1j * r.standard_normal(1 << n)).astype(np.complex128)
+    return s / np.linalg.norm(s)
+
+
+def jit_source(plan, host):
+    need = ctypes.c_size_t()
+    check(lib.hq_debug_group_plan_jit_source(plan, int(host), None, 0, ctypes.byref(need)))
+    buf = ctypes.create_string_buffer(need.value)
+    check(lib.hq_debug_group_plan_jit_source(plan, int(host), buf, need.value, ctypes.byref(need)))
+    return buf.value.decode()
+
+
+def run_host_flavour(src, state):
+    with tempfile.TemporaryDirectory() as d:
+        cpp, so = os.path.join(d, "k.cpp"), os.path.join(d, "k.so")
+        open(cpp, "w").write(src)
+        # -ffp-contract=off: the host build must not fuse what the source does not fuse
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", cpp, "-o", so])
+        k = ctypes.CDLL(so)
+        k.hq_group_jit_host.argtypes = [ctypes.c_void_p]
+        k.hq_group_jit_host(state.ctypes.data)
+
+
+def make_plan(n, mask, gates):
+    plan = ctypes.c_void_p()
+    check(lib.hq_group_plan_create(n, mask, pack(gates), len(gates), ctypes.byref(plan)))
+    return plan
+
+
+@pytest.mark.parametrize("n,K,seed", [(12, 10, 0), (13, 11, 1), (14, 12, 2), (15, 12, 3), (12, 12, 4), (16, 11, 5)])
+def test_specialised_source_matches_oracle(n, K, seed):
+    rng = random.Random(seed)
+    rest = list(range(3, n))
+    rng.shuffle(rest)
+    tile = [0, 1, 2] + sorted(rest[:K - 3])
+    mask = sum(1 << b for b in tile)
+    _, gates = O.parse_qasm(C.random_circuit(n, 250, seed))
+    keep = [g for g in gates if (g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target in tile]
+    plan = make_plan(n, mask, keep)
+    st = random_state(n, seed)
+    want = st.copy()
+    O.apply(want, n, keep)
+    run_host_flavour(jit_source(plan, True), st)
+    lib.hq_group_plan_destroy(plan)
+    assert np.max(np.abs(st - want)) < 1e-13
+
+
+def test_specialised_source_supremacy_like_and_fixed_bits():
+    """CZ / T / butterfly mixes (the sign-flip and deferred-scale paths) on a chunked launch (fixed bits)."""
+    n, fixed_bit = 15, 13
+    text = C.supremacy(n, cycles=12, seed=5)
+    _, gates = O.parse_qasm(text)
+    mask = 0xFFF
+    keep = [g for g in gates if fixed_bit not in (g.target, g.control, g.control2)
+            and ((g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target < 12)]
+    st = random_state(n, 1)
+    want = st.copy()
+    O.apply(want, n, keep)
+    for value in (0, 1):
+        plan = ctypes.c_void_p()
+        check(lib.hq_group_plan_create_ex(n, mask, 1 << fixed_bit, value << fixed_bit, pack(keep), len(keep), ctypes.byref(plan)))
+        run_host_flavour(jit_source(plan, True), st)
+        lib.hq_group_plan_destroy(plan)
+    assert np.max(np.abs(st - want)) < 1e-13
+
+
+def test_free_gates_emit_no_fp64():
+    """X / Y / Z / S / CNOT / CZ on register qubits are renamings: the emitter's own instruction count stays 0."""
+    gates = [O.OGate("x", 5), O.OGate("y", 6), O.OGate("z", 7), O.OGate("s", 8), O.OGate("cx", 6, 5), O.OGate("cz", 7, 8)]
+    plan = make_plan(13, 0xFFF, gates)
+    src = jit_source(plan, False)
+    lib.hq_group_plan_destroy(plan)
+    m = re.search(r"fp64 instructions per thread per tile: (\d+)", src)
+    assert m and int(m.group(1)) == 0, src[-200:]
+
+
+def test_cuda_flavour_compiles_for_sm100a(tmp_path):
+    n = 14
+    _, gates = O.parse_qasm(C.random_circuit(n, 120, 3))
+    keep = [g for g in gates if (g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target < 12]
+    plan = make_plan(n, 0xFFF, keep)
+    src = jit_source(plan, False)
+    lib.hq_group_plan_destroy(plan)
+    log = ctypes.create_string_buffer(1 << 16)
+    out = str(tmp_path / "k.cubin")
+    rc = lib.hq_debug_jit_compile_to_file(src.encode(), out.encode(), log, len(log))
+    if rc != 0 and b"libnvrtc not found" in log.value:
+        pytest.skip("NVRTC not installed on this machine")
+    assert rc == 0, log.value.decode()[:2000]
+    info = log.value.decode()
+    m = re.search(r"Used (\d+) registers", info)
+    assert m and int(m.group(1)) <= 128, info
+    assert "bytes spill stores" not in info or re.search(r"\b0 bytes spill stores", info), info
+    assert os.path.getsize(out) > 1000
