@@ -61,6 +61,7 @@ _SIGS = {
     "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
     "hq_group_plans_warm": (_c.c_int, [_P(_c.c_void_p), _c.c_int]),
     "hq_group_plan_is_specialised": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
+    "hq_jit_available": (_c.c_int, [_P(_c.c_int)]),
     "hq_jit_stats": (_c.c_int, [_P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_double)]),
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
     "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),

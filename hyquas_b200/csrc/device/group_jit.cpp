@@ -429,9 +429,15 @@ struct Emitter {
 
 }  // namespace
 
-int jit_min_blocks(int K) { return K == 12 ? 2 : (K == 11 ? 4 : 8); }
+int jit_min_blocks(int K) { return K == 12 ? 1 : (K == 11 ? 2 : 4); }   // CTAs (of two workers, three buffers) per SM
+size_t jit_smem_bytes(int K) { return (size_t)3 * (16u << K) + 64; }
 
-// Skeleton of the device kernel: identical in structure to group_kernel<K> (group_kernel.cu), constants baked in.
+// Skeleton of the device kernel.  Same tile pipeline as group_kernel<K> (group_kernel.cu) with one change that ncu asked for
+// (profiles/r02_s1: 38 % of all stall samples sat in the "tile landed" wait, DRAM at 4.4 TB/s): a CTA is TWO workers of NT
+// threads that share THREE tile buffers.  Tiles ("slots") of a CTA are processed alternately by the two workers; slot s lives
+// in buffer s % 3 and its TMA load is issued by the worker that empties that buffer (slot s - 3, when its last round has pulled
+// the amplitudes into registers).  So while both workers compute, the third buffer is being filled: a load is in flight for a
+// whole tile-time instead of one round.  Workers synchronise among themselves with named barriers (bar.sync 1 + worker).
 const char* jit_device_prologue() {
     return R"SRC(
 typedef unsigned long long u64;
@@ -443,12 +449,9 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
                  :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* tile, u64* bar, u64* tbase_s, u32 lane) {
+__device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* tile, u64* bar, u32 lane) {
     const u64 base = HQ_TILE_BASE(t);
-    if (lane == 0) {
-        *tbase_s = base;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(TILE * 16) : "memory");
-    }
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(TILE * 16) : "memory");
     __syncwarp();
     for (u32 q = lane; q < NRUNS; q += 32)
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -457,28 +460,31 @@ __device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* 
 #define HQ_LD(idx, a, b) { const double2 q_ = tile[idx]; a = q_.x; b = q_.y; }
 #define HQ_ST(idx, a, b) tile[idx] = make_double2(a, b)
 #define HQ_ST_GLOBAL(idx, a, b) state[idx] = make_double2(a, b)
-#define HQ_SYNC() __syncthreads()
+#define HQ_SYNC() asm volatile("bar.sync %0, %1;" :: "r"(wk + 1), "n"(NT) : "memory")
 #define HQ_SYNCWARP() __syncwarp()
 #define HQ_ROUND_DONE()
-// every thread holds its amplitudes in registers: the buffer can take the next tile now (its HBM read runs under the arithmetic)
-#define HQ_TILE_CONSUMED() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncthreads(); \
-        const u64 tn = t + gridDim.x; if (tn < NTILES && tid < 32) issue_tile_load(state, tn, tile, bar, tbase_s, tid); }
-extern "C" __global__ void __launch_bounds__(NT, MINB) hq_group_jit(double2* __restrict__ state) {
+// every thread of the worker holds its amplitudes in registers: the buffer can take the tile three slots ahead
+#define HQ_TILE_CONSUMED() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); HQ_SYNC(); \
+        if (s + 3 < nslots && tid < 32) issue_tile_load(state, (u64)blockIdx.x + (u64)(s + 3) * gridDim.x, tile, bar + b, tid); }
+extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2* __restrict__ state) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2* tile = reinterpret_cast<double2*>(smem_raw);
-    u64* bar = reinterpret_cast<u64*>(smem_raw + (size_t)TILE * 16);
-    u64* tbase_s = bar + 1;
-    const u32 tid = threadIdx.x;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(1));
+    u64* bar = reinterpret_cast<u64*>(smem_raw + (size_t)3 * TILE * 16);
+    const u32 tid = threadIdx.x & (NT - 1);
+    const u32 wk = threadIdx.x / NT;
+    const u32 nslots = blockIdx.x < NTILES ? (u32)((NTILES - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;   // tiles of this CTA
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar + i)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    u64 t = blockIdx.x;
-    if (t < NTILES && tid < 32) issue_tile_load(state, t, tile, bar, tbase_s, tid);
-    for (u32 it = 0; t < NTILES; t += gridDim.x, ++it) {
-      mbar_wait(bar, it & 1);
-      const u64 tbase = *tbase_s;
+    if (threadIdx.x < 32)
+        for (u32 i = 0; i < 3 && i < nslots; ++i)
+            issue_tile_load(state, (u64)blockIdx.x + (u64)i * gridDim.x, reinterpret_cast<double2*>(smem_raw + (size_t)i * TILE * 16), bar + i, threadIdx.x);
+    for (u32 s = wk; s < nslots; s += 2) {
+      const u32 b = s % 3u;
+      double2* tile = reinterpret_cast<double2*>(smem_raw + (size_t)b * TILE * 16);
+      mbar_wait(bar + b, (s / 3u) & 1u);
+      const u64 tbase = HQ_TILE_BASE((u64)blockIdx.x + (u64)s * gridDim.x);
 )SRC";
 }
 const char* jit_device_epilogue() { return "    }\n}\n"; }

@@ -12,6 +12,7 @@ namespace hq {
 // Empty string: the emitter does not handle this plan (the interpreter kernel does).
 std::string jit_emit_source(const hq_group_plan& plan, bool host);
 int jit_min_blocks(int K);
+size_t jit_smem_bytes(int K);   // dynamic shared memory of the kernel: three tile buffers + mbarriers
 const char* jit_device_prologue();
 const char* jit_device_epilogue();
 const char* jit_host_prologue();

@@ -364,6 +364,12 @@ extern "C" int hq_debug_jit_compile_to_file(const char* source, const char* path
     return out ? HQ_OK : HQ_ERR_ARG;
 }
 
+// 1 when gate groups will run as specialised kernels: HQ_JIT not 0 and NVRTC loadable (no GPU needed to answer)
+extern "C" int hq_jit_available(int* yes) {
+    if (yes) *yes = hq::jit_enabled() && hq::nvrtc().ok();
+    return HQ_OK;
+}
+
 extern "C" int hq_jit_stats(int* kernels_loaded, int* compiled, int* disk_hits, double* compile_seconds) {
     hq::jit_stats(kernels_loaded, compiled, disk_hits, compile_seconds);
     return HQ_OK;

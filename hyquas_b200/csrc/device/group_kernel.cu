@@ -782,7 +782,7 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
 static void resolve_jit(const hq_group_plan* plan) {
     if (plan->jit || plan->jit_failed || plan->jit_source.empty()) return;
     std::string why;
-    const size_t smem = (size_t)(16u << plan->K) + 16;
+    const size_t smem = jit_smem_bytes(plan->K);
     JitKernel* k = jit_get(plan->jit_source, smem, &why);
     if (!k) {
         plan->jit_failed = true;
@@ -791,7 +791,7 @@ static void resolve_jit(const hq_group_plan* plan) {
         return;
     }
     plan->jit = k;
-    plan->jit_occupancy = jit_max_blocks_per_sm(k, plan->NT, smem);
+    plan->jit_occupancy = jit_max_blocks_per_sm(k, 2 * plan->NT, smem);
 }
 
 extern "C" int hq_group_plans_warm(hq_group_plan* const* plans, int n) {
@@ -841,8 +841,9 @@ extern "C" int hq_group_plan_launch(const hq_group_plan* plan, void* state, int 
     cudaStream_t s = on_comm_stream ? rt().comm : rt().compute;
     resolve_jit(plan);
     if (plan->jit) {
-        plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * plan->jit_occupancy - rt().reserved_ctas));
-        return jit_launch(static_cast<JitKernel*>(plan->jit), plan->grid, plan->NT, (size_t)(16u << plan->K) + 16, s, state);
+        // a CTA = two workers: at least two tiles per CTA when there are enough of them
+        plan->grid = (int)std::min<uint64_t>((p.ntiles + 1) / 2, (uint64_t)std::max(1, rt().sm_count * plan->jit_occupancy - rt().reserved_ctas));
+        return jit_launch(static_cast<JitKernel*>(plan->jit), plan->grid, 2 * plan->NT, jit_smem_bytes(plan->K), s, state);
     }
     const bool relaxed = rt().relaxed_regs;   // fewer resident CTAs, no register cap (HQ_RELAXED_REGS=1)
     // resident CTAs per SM asked of ptxas: 2048 threads' worth of registers at 64 (RBITS=3) / 128 (RBITS=4) per thread

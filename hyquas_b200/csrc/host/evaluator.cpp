@@ -16,7 +16,7 @@ Evaluator::Evaluator() {
     // a gate-group launch of G same-type gates takes  max(sweep, groupBaseMs30 + G * gate cost + extra rounds * roundMs30);
     // a fused dense launch takes  max(sweep, denseBaseMs30 + sum of per-matrix costs).  tools/calibrate.py rewrites them
     // from a fresh microbenchmark run ($HYQUAS_PARAM_FILE).
-    hbmGBs = 5915.0;        // one in-place sweep (16 B read + 16 B written per amplitude): 5.8 ms per 2^30
+    hbmGBs = 6250.0;        // one in-place sweep (16 B read + 16 B written per amplitude): 5.5 ms per 2^30
     launchMs = 0.01;
     nvlinkGBs = 700.0;
     groupBaseMs30 = 2.6;
@@ -36,6 +36,15 @@ Evaluator::Evaluator() {
     set(GateType::CZ, 0.10); set(GateType::CU1, 0.10); set(GateType::CRZ, 0.25);
     set(GateType::CNOT, 0.25); set(GateType::CY, 0.27); set(GateType::CCX, 0.25);
     set(GateType::CRX, 0.33); set(GateType::CRY, 0.33);
+    // specialised kernels (profiles/r02_s1_microbench_jit.json): 64..256 butterflies run at 0.134-0.138 ms each (2 FP64
+    // instructions per amplitude, 85-92 % of the 18.6 T instr/s peak), 64 U3 at 0.356 ms each (6 per amplitude); permutations,
+    // CZ / Z / S and diagonal runs on thread bits ride the 5.5 ms sweep
+    int avail = 0;
+    hq_jit_available(&avail);
+    specialised = avail != 0;
+    instrMs30 = 0.066;
+    jitRoundMs30 = 0.4;
+    jitBaseMs30 = 0.3;
     const double dense[8] = {2.75, 2.75, 2.75, 2.75, 5.0, 9.7, 18.3, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
     for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
 }
@@ -59,6 +68,10 @@ void Evaluator::loadParam(int) {
         else if (key == "round_ms30") in >> roundMs30;
         else if (key == "circuit_factor") in >> circuitFactor;
         else if (key == "group_base_ms30") in >> groupBaseMs30;
+        else if (key == "instr_ms30") in >> instrMs30;
+        else if (key == "jit_round_ms30") in >> jitRoundMs30;
+        else if (key == "jit_base_ms30") in >> jitBaseMs30;
+        else if (key == "specialised") { int v; in >> v; specialised = v != 0; }
         else if (key == "dense_base_ms30") in >> denseBaseMs30;
         else if (key == "gate") { int i; double v; in >> i >> v; if (i >= 0 && i < 32) gateNs[i] = v; }
         else if (key == "dense") { int i; double v; in >> i >> v; if (i >= 0 && i < 8) denseMs30[i] = v; }
@@ -74,8 +87,12 @@ double Evaluator::perfPerGate(int numQubits, const std::vector<GateType>& types)
 
 // alpha * [[1, p], [q, -p q]] with p, q both in {+-1} or both in {+-i}, uncontrolled: the tile kernel's butterfly class
 // (same test as classify() in device/group_kernel.cu): H, RX(+-pi/2), RY(+-pi/2) whatever their type tag says.
+static bool isButterflyMat(const Gate& g);
 static bool isButterfly(const Gate& g) {
     if (g.controlQubit != -1 || g.controlQubit2 != -1) return false;
+    return isButterflyMat(g);
+}
+static bool isButterflyMat(const Gate& g) {
     typedef std::complex<double> C;
     const C a(g.mat[0][0].x, g.mat[0][0].y), b(g.mat[0][1].x, g.mat[0][1].y), c(g.mat[1][0].x, g.mat[1][0].y), d(g.mat[1][1].x, g.mat[1][1].y);
     if (std::abs(a) < 0.5) return false;
@@ -84,9 +101,57 @@ static bool isButterfly(const Gate& g) {
     return ((unit(p, false) && unit(q, false)) || (unit(p, true) && unit(q, true))) && std::abs(r + p * q) < 1e-14;
 }
 
+// FP64 instructions per amplitude the specialised kernel emits for this gate (device/group_jit.cpp: every scalar is
+// coefficient x variable, a sum of n terms costs n - 1 instructions, products by constants are free until the round's flush).
+double Evaluator::instrPerAmp(const Gate& g) {
+    int nz[2] = {0, 0};
+    bool unit = true;   // every non-zero entry is +-1 or +-i
+    for (int r = 0; r < 2; r++)
+        for (int c = 0; c < 2; c++) {
+            const qComplex z = g.mat[r][c];
+            if (z.x == 0.0 && z.y == 0.0) continue;
+            nz[r]++;
+            if (!((std::fabs(z.x) == 1.0 && z.y == 0.0) || (z.x == 0.0 && std::fabs(z.y) == 1.0))) unit = false;
+        }
+    double cost;
+    if (nz[0] <= 1 && nz[1] <= 1) {
+        // permutation / diagonal: a non-unit entry (x + iy)(a + ib) is one instruction per scalar of the half it multiplies
+        // (plus its share of the round's flush)
+        if (unit) cost = 0.02;
+        else {
+            const bool d0one = g.mat[0][0].x == 1.0 && g.mat[0][0].y == 0.0 && g.mat[0][1].x == 0.0 && g.mat[0][1].y == 0.0;
+            cost = d0one ? 1.0 : 2.0;
+        }
+    } else {
+        // dense 2x2: real, RX-like (and butterflies): each output scalar is a sum of 2 terms; general complex: 4 terms
+        bool realLike = true, rxLike = true;
+        for (int r = 0; r < 2; r++)
+            for (int c = 0; c < 2; c++) {
+                const qComplex z = g.mat[r][c];
+                if (z.y != 0.0) realLike = false;
+                if ((r == c ? z.y : z.x) != 0.0) rxLike = false;
+            }
+        cost = (realLike || rxLike || isButterflyMat(g)) ? 2.0 : 6.0;
+    }
+    if (g.controlQubit >= 0) cost *= 0.5;
+    if (g.controlQubit2 >= 0) cost *= 0.5;
+    return cost;
+}
+
 // With the gates at hand the number of register rounds can be bounded from below: a round holds 4 register qubits.
 double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
     loadParam(numQubits);
+    if (specialised) {
+        double instr = 0;
+        qindex targets = 0;
+        for (const Gate& g : gates) {
+            instr += instrPerAmp(g);
+            if (!g.isDiagonal()) targets |= qindex(1) << g.targetQubit;
+        }
+        const int rounds = std::max(1, (bitCount(targets) + 3) / 4);
+        const double compute = jitBaseMs30 + instrMs30 * instr + jitRoundMs30 * (rounds - 1);
+        return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
+    }
     double compute = groupBaseMs30;
     qindex targets = 0;
     for (const Gate& g : gates) {

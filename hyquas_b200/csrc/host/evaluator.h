@@ -38,6 +38,13 @@ public:
     double circuitFactor;                   // in-circuit / microbenchmark cost ratio of the tile kernel's gate work (fit)
     double denseMs30[8];                    // fused dense kernel, per 2^30 amplitudes, indexed by matrix qubits
     double launchMs;                        // fixed per-launch overhead
+    // specialised (JIT) tile kernels: a gate costs the FP64 instructions per amplitude its matrix needs (0 for permutations and
+    // +-1 / +-i phases, 2 for butterflies and real / RX-like 2x2, 6 for a general complex 2x2, 1 per multiplied half for a phase)
+    bool specialised;                       // price tile groups for the specialised kernels (hq_jit_available)
+    double instrMs30;                       // ms per (FP64 instruction per amplitude) over 2^30 amplitudes
+    double jitRoundMs30;                    // coefficient flush + shared-memory exchange of one extra round
+    double jitBaseMs30;
+    static double instrPerAmp(const Gate& g);
 private:
     Evaluator();
     bool loaded = false;

@@ -93,6 +93,7 @@ int hq_group_plan_destroy(hq_group_plan* plan);
  * schedule's plans at once compiles the cache misses on all host cores. */
 int hq_group_plans_warm(hq_group_plan* const* plans, int n);
 int hq_group_plan_is_specialised(const hq_group_plan* plan, int* yes);
+int hq_jit_available(int* yes);   /* HQ_JIT not 0 and NVRTC loadable; the evaluator prices tile groups accordingly */
 int hq_jit_stats(int* kernels_loaded, int* compiled, int* disk_hits, double* compile_seconds);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 
