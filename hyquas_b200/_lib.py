@@ -106,6 +106,7 @@ _SIGS = {
     "hq_circuit_prepare_state": (_c.c_int, [_c.c_void_p]),
     "hq_circuit_execute": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_double), _P(_c.c_float), _c.c_int, _P(_c.c_int)]),
     "hq_circuit_norm2": (_c.c_int, [_c.c_void_p, _P(_c.c_double)]),
+    "hq_circuit_swap_alone_ms": (_c.c_int, [_c.c_void_p, _P(_c.c_double)]),
     "hq_circuit_io_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_size_t), _P(_c.c_size_t)]),
     "hq_circuit_schedule_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
     "hq_circuit_group_info": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_double), _P(_c.c_int), _P(_c.c_int)]),

@@ -438,6 +438,11 @@ size_t jit_smem_bytes(int K) { return (size_t)3 * (16u << K) + 64; }
 // in buffer s % 3 and its TMA load is issued by the worker that empties that buffer (slot s - 3, when its last round has pulled
 // the amplitudes into registers).  So while both workers compute, the third buffer is being filled: a load is in flight for a
 // whole tile-time instead of one round.  Workers synchronise among themselves with named barriers (bar.sync 1 + worker).
+// "Landed" mbarriers: SIX, slot s uses s % 6 (two per buffer, alternating).  With one per buffer the other worker can reach its
+// wait for slot s + 3 while slot s is still in flight (tiny tiles, it is the one that issued slot s two short tile-times
+// ago); a parity wait cannot tell "one phase ahead" from "one phase behind" and would fall through on stale data.  With two
+// per buffer the barrier of slot s + 3 is idle until its own load is issued, and slot s + 6 belongs to the same worker as
+// slot s, which has consumed it by then.
 const char* jit_device_prologue() {
     return R"SRC(
 typedef unsigned long long u64;
@@ -465,7 +470,7 @@ __device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* 
 #define HQ_ROUND_DONE()
 // every thread of the worker holds its amplitudes in registers: the buffer can take the tile three slots ahead
 #define HQ_TILE_CONSUMED() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); HQ_SYNC(); \
-        if (s + 3 < nslots && tid < 32) issue_tile_load(state, (u64)blockIdx.x + (u64)(s + 3) * gridDim.x, tile, bar + b, tid); }
+        if (s + 3 < nslots && tid < 32) issue_tile_load(state, (u64)blockIdx.x + (u64)(s + 3) * gridDim.x, tile, bar + (s + 3) % 6u, tid); }
 extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2* __restrict__ state) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* bar = reinterpret_cast<u64*>(smem_raw + (size_t)3 * TILE * 16);
@@ -473,7 +478,7 @@ extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2*
     const u32 wk = threadIdx.x / NT;
     const u32 nslots = blockIdx.x < NTILES ? (u32)((NTILES - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;   // tiles of this CTA
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar + i)), "r"(1));
+        for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar + i)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -483,7 +488,7 @@ extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2*
     for (u32 s = wk; s < nslots; s += 2) {
       const u32 b = s % 3u;
       double2* tile = reinterpret_cast<double2*>(smem_raw + (size_t)b * TILE * 16);
-      mbar_wait(bar + b, (s / 3u) & 1u);
+      mbar_wait(bar + s % 6u, (s / 6u) & 1u);
       const u64 tbase = HQ_TILE_BASE((u64)blockIdx.x + (u64)s * gridDim.x);
 )SRC";
 }

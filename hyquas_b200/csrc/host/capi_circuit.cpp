@@ -8,6 +8,7 @@
 #include "logger.h"
 #include "qasm.h"
 #include "compiler.h"
+#include "peephole.h"
 
 struct hq_circuit {
     std::unique_ptr<Circuit> c;
@@ -49,6 +50,20 @@ extern "C" int hq_circuit_add_gate(hq_circuit* h, int type, int control2, int co
     const int n = h->c->numQubits;
     for (int q : {control2, control}) if (q < -1 || q >= n) { g_cerr = "control out of range"; return HQ_ERR_ARG; }
     if (target < 0 || target >= n) { g_cerr = "target out of range"; return HQ_ERR_ARG; }
+    {   // operands must be distinct, and a controlled type needs its control(s)
+        const GateType t = (GateType)type;
+        const bool two = t == GateType::CCX;
+        const bool one = t == GateType::CNOT || t == GateType::CY || t == GateType::CZ || t == GateType::CRX || t == GateType::CRY ||
+                         t == GateType::CU1 || t == GateType::CRZ;
+        if ((one || two) && control < 0) { g_cerr = "controlled gate without a control qubit"; return HQ_ERR_ARG; }
+        if (two && control2 < 0) { g_cerr = "ccx needs two control qubits"; return HQ_ERR_ARG; }
+        if (!one && !two && (control >= 0 || control2 >= 0)) { g_cerr = "control qubit given to an uncontrolled gate type"; return HQ_ERR_ARG; }
+        if (!two && control2 >= 0) { g_cerr = "second control given to a singly controlled gate type"; return HQ_ERR_ARG; }
+        if ((control >= 0 && control == target) || (control2 >= 0 && (control2 == target || control2 == control))) {
+            g_cerr = "gate operands must be distinct qubits";
+            return HQ_ERR_ARG;
+        }
+    }
     Gate g;
     switch ((GateType)type) {
         case GateType::CCX: g = Gate::CCX(control, control2, target); break;
@@ -84,6 +99,8 @@ extern "C" int hq_circuit_num_gates(const hq_circuit* h) { return h ? (int)h->c-
 
 extern "C" int hq_circuit_compile(hq_circuit* h) {
     if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    g_cerr = h->c->compileError();   // what the CLI reports with exit(1) is an error code for an embedding host
+    if (!g_cerr.empty()) return HQ_ERR_ARG;
     h->c->compile();
     return HQ_OK;
 }
@@ -91,7 +108,9 @@ extern "C" int hq_circuit_compile(hq_circuit* h) {
 // host-only: run the partitioner without touching a GPU and report the shape of the schedule
 extern "C" int hq_circuit_plan_only(hq_circuit* h, int* stages, int* groups, int* swapped_bits) {
     if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
-    Compiler compiler(h->c->numQubits, h->c->getGates());
+    g_cerr = h->c->compileError();
+    if (!g_cerr.empty()) return HQ_ERR_ARG;
+    Compiler compiler(h->c->numQubits, hyquas::peephole(h->c->getGates(), nullptr));   // what compile() partitions
     Schedule s = compiler.run();
     if (stages) *stages = (int)s.localGroups.size();
     if (groups) *groups = s.numGroups();
@@ -127,6 +146,12 @@ extern "C" int hq_circuit_execute(hq_circuit* h, int* time_us, double* device_ms
 extern "C" int hq_circuit_norm2(hq_circuit* h, double* out) {
     if (!h || !out) { g_cerr = "null argument"; return HQ_ERR_ARG; }
     *out = h->c->norm2();
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_swap_alone_ms(hq_circuit* h, double* ms) {
+    if (!h || !ms) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    *ms = h->c->swapAloneMs();
     return HQ_OK;
 }
 

@@ -28,11 +28,23 @@ void Circuit::destroyState() {
     deviceStateVec.clear();
 }
 
+std::string Circuit::compileError() const {
+    // The tile kernel works on tiles of >= 2^10 amplitudes (the reference's LOCAL_QUBIT_SIZE = 10, utils.h:45).  One process
+    // can fall back to the dense kernel for 9 local qubits; with global qubits a group may hold gates whose controls sit on
+    // global or fixed bits, which only the tile kernel resolves, so 10 local qubits are required there.
+    const int L = numQubits - MyGlobalVars::bit;
+    const int need = MyGlobalVars::bit > 0 ? 10 : 9;
+    if (L >= need) return "";
+    char buf[200];
+    snprintf(buf, sizeof(buf), "hyquas_b200: %d qubits on %d GPU(s) leaves %d local qubits; at least %d are needed", numQubits,
+             MyGlobalVars::numGPUs, L, need);
+    return buf;
+}
+
 void Circuit::compile() {
-    if (numQubits - MyGlobalVars::bit < 9) {
-        // the kernels work on tiles of >= 2^9 amplitudes per GPU (the reference's tile is LOCAL_QUBIT_SIZE = 10 qubits, utils.h:45)
-        printf("hyquas_b200: %d qubits on %d GPU(s) leaves %d local qubits; at least 9 are needed\n", numQubits, MyGlobalVars::numGPUs,
-               numQubits - MyGlobalVars::bit);
+    const std::string bad = compileError();
+    if (!bad.empty()) {
+        printf("%s\n", bad.c_str());
         exit(1);
     }
     auto t0 = chrono::system_clock::now();
@@ -134,6 +146,25 @@ int Circuit::run(bool copy_back, bool destroy) {
     return us;
 }
 
+// The schedule's exchanges alone, back to back, nothing computing: the denominator of "how much of the swap is hidden".
+// The data is left wherever the exchanges put it: call it on a state that is not needed any more.
+double Circuit::swapAloneMs() {
+    if (deviceStateVec.empty() || MyGlobalVars::numGPUs == 1) return 0.0;
+    checkHq(hq_sync());
+    checkHq(hq_timer_start());
+    for (size_t s = 1; s < schedule.localGroups.size(); s++) {
+        LocalGroup& lg = schedule.localGroups[s];
+        if (lg.swap.empty()) continue;
+        hyquas::SwapExec ex(deviceStateVec[0], numQubits - MyGlobalVars::bit, lg.swap, lg.swapPlan);
+        ex.begin();
+        for (int i = 0; i < (1 << lg.swap.localBit.size()); i++) ex.waitNextChunk();
+        ex.end();
+    }
+    float ms = 0;
+    checkHq(hq_timer_stop_ms(&ms));
+    return ms;
+}
+
 double Circuit::norm2() {
     double v = 0;
     if (!deviceStateVec.empty()) checkHq(hq_state_norm2(deviceStateVec[0], numQubits - MyGlobalVars::bit, &v));
@@ -194,9 +225,11 @@ qComplex Circuit::ampAtGPU(qindex idx) {
 }
 
 ResultItem Circuit::ampAt(qindex idx) {
-    const int L = numQubits - MyGlobalVars::bit;
+    // With more than one process every rank must take the same path: ampAtGPU ends in a broadcast from the owner (the
+    // reference's is a symmetric MPI_Bcast, src/circuit.cpp:95-125).  The host-side shortcuts are single-process only.
+    if (MyGlobalVars::numGPUs > 1) return ResultItem(idx, ampAtGPU(idx));
     const qindex id = toPhysicalID(idx);
-    if (!result.empty() && (id >> L) == MyMPI::rank) return ResultItem(idx, result[id & ((qindex(1) << L) - 1)]);
+    if (!result.empty()) return ResultItem(idx, result[id]);
     if (idx < 128 && dumpItems.size() >= 128) return dumpItems[idx];
     return ResultItem(idx, ampAtGPU(idx));
 }

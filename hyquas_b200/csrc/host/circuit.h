@@ -42,6 +42,8 @@ public:
     bool fullState(std::vector<qComplex>& out);              // all 2^n amplitudes in LOGICAL order (single process, small n)
     bool localShard(double* out);                            // this process' amplitudes in PHYSICAL order
     double norm2();                                          // sum |a|^2 over this process' shard
+    double swapAloneMs();                                    // the schedule's exchanges with no compute (collective)
+    std::string compileError() const;                        // why compile() would refuse (empty: it would not)
     size_t planBytes() const;                                // bytes of device tables uploaded by compile()
     size_t dumpBytes() const { return dumpItems.size() * sizeof(ResultItem); }
     const Schedule& getSchedule() const { return schedule; }

@@ -111,6 +111,9 @@ SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal, b
 
 Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
     : numQubits(numQubits_), numLocal(numQubits_ - MyGlobalVars::bit), gates(std::move(inputGates)) {
+    // the partitioner matches gates by id (dense pick, deferral): ids are positions in THIS list, whatever the caller's Gate
+    // objects carried (a Gate added twice keeps one gateID in the reference's scheme, src/gate.cpp:7)
+    for (size_t i = 0; i < gates.size(); i++) gates[i].gateID = (int)i;
     tileBits = std::min(hq_group_tile_bits(), numLocal);
     pinnedBits = std::min(5, tileBits);   // planSwap relies on pinnedBits <= 5
     if (const char* e = getenv("HQ_PINNED_BITS")) pinnedBits = std::max(hq_group_min_run_bits(), std::min(atoi(e), std::min(5, tileBits)));
@@ -124,12 +127,10 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
     overlapSlack = 1.0;
     if (const char* e = getenv("HQ_OVERLAP_SLACK")) overlapSlack = atof(e);
     enableOverlap = true;
-    overlapSplit = false;
     if (const char* e = getenv("HQ_ENABLE_OVERLAP")) enableOverlap = atoi(e) != 0;
     if (const char* e = getenv("HQ_OVERLAP_MODE")) {
         const std::string v = e;
         if (v == "off") enableOverlap = false;
-        overlapSplit = v == "split";
     }
     cutBothWays = true;
     if (const char* e = getenv("HQ_CUT_BOTH_WAYS")) cutBothWays = atoi(e) != 0;
@@ -403,59 +404,54 @@ Schedule Compiler::run() {
     }
     // pass 2: work to hide the exchange behind.  The stage split is greedy, so the head of stage s always needs the
     // incoming qubits; what CAN run while chunks are still on the wire is the tail of stage s-1 (the reference's moveToNext
-    // + overlapGroups, src/compiler.cpp:34-68, src/executor.cpp:41-47).  Only WHOLE trailing groups of stage s-1 are
-    // deferred past the swap -- the sweep count stays what it was, those sweeps merely move under the exchange -- and only
-    // as many as the predicted exchange time hides.  A group qualifies when every non-diagonal target avoids the swapped
-    // positions in the NEW layout and it still fits one launch there.
+    // + overlapGroups, src/compiler.cpp:34-68, src/executor.cpp:41-47), run chunk by chunk as the chunks land.
     for (size_t s = 1; s < stages.size() && enableOverlap; s++) {
         LocalGroup& lg = schedule.localGroups[s];
         const int k = (int)lg.swap.localBit.size();
-        if (k == 0 || numLocal - k < 8) continue;
+        if (k == 0 || numLocal - k < 10) continue;   // a per-chunk launch needs a 10-bit tile of varying positions
         qindex lowSet = 0, exclude = 0;
         for (int b : lg.swap.localBit) exclude |= qindex(1) << b;
         for (int p = 0; p < numLocal; p++) if (!(exclude >> p & 1)) lowSet |= qindex(1) << lg.state.layout[p];
         std::vector<Gate>& prev = stages[s - 1].gates;
-        const double commMs = Evaluator::getInstance()->perfSwap(numLocal, k);
-        double used = 0;
-        std::vector<int> ids;
-        if (overlapSplit) {
-            // "split" variant (HQ_OVERLAP_MODE=split): defer the maximal suffix-closed set of gates that avoid the swapped
-            // positions, re-cut into per-chunk groups.  Hides more, but the re-cut may add sweeps to the schedule.
-            std::vector<int> order(prev.size());
-            for (size_t i = 0; i < order.size(); i++) order[i] = (int)prev.size() - 1 - (int)i;   // scan from the end
-            std::vector<int> tail = hyquas::runnableGates(prev, order, lowSet, 1 << 30);
-            std::sort(tail.begin(), tail.end());
-            std::vector<Gate> tailGates;
-            for (int gi : tail) tailGates.push_back(prev[gi]);
-            std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
-            size_t first = cand.size();
-            while (first > 0) {   // longest suffix of the candidate groups that fits under the exchange
-                const double ms = cand[first - 1].predictedMs * (1 << k);
-                if (used + ms > commMs * overlapSlack) break;
-                used += ms;
-                first--;
-            }
-            for (size_t i = first; i < cand.size(); i++) {
-                for (auto& g : cand[i].gates) ids.push_back(g.gateID);
-                lg.overlapGroups.push_back(cand[i]);
-            }
+        Evaluator* ev = Evaluator::getInstance();
+        const double commMs = ev->perfSwap(numLocal, k);
+        auto total = [](const std::vector<GateGroup>& gs) { double t = 0; for (auto& g : gs) t += g.predictedMs; return t; };
+        // Gate-granular deferral (the reference's moveToNext, src/compiler.cpp:34-68): the maximal suffix-closed set of stage
+        // s-1's gates whose non-diagonal targets stay local and off the swapped positions, re-cut into per-chunk groups in the
+        // NEW layout.  Any suffix of that group sequence is itself suffix-closed, so the choice is how many trailing groups
+        // to defer: the one that minimises the predicted  (what is left of stage s-1) + max(exchange, deferred work),
+        // i.e. deferral is taken only where it does not cost more in extra sweeps than it hides.
+        std::vector<int> order(prev.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)prev.size() - 1 - (int)i;   // scan from the end
+        std::vector<int> tail = hyquas::runnableGates(prev, order, lowSet, 1 << 30);
+        std::sort(tail.begin(), tail.end());
+        std::vector<Gate> tailGates;
+        for (int gi : tail) tailGates.push_back(prev[gi]);
+        if (tailGates.empty()) continue;
+        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
+        const State& prevState = schedule.localGroups[s - 1].state;
+        const double underExchange = 1.15;   // per-chunk launches share SMs and HBM with the exchange kernel
+        double bestCost = total(cutGroups(prev, prevState, numLocal, 0)) + commMs;
+        size_t bestFirst = cand.size();
+        double deferredMs = 0;
+        for (size_t first = cand.size(); first-- > 0;) {
+            deferredMs += cand[first].predictedMs * (1 << k) * underExchange;   // predictedMs is per chunk
+            if (deferredMs > commMs * overlapSlack * 1.5) break;
+            std::vector<int> ids;
+            for (size_t i = first; i < cand.size(); i++) for (auto& g : cand[i].gates) ids.push_back(g.gateID);
+            std::sort(ids.begin(), ids.end());
+            std::vector<Gate> rest;
+            for (auto& g : prev) if (!std::binary_search(ids.begin(), ids.end(), g.gateID)) rest.push_back(g);
+            const double cost = total(cutGroups(rest, prevState, numLocal, 0)) + std::max(commMs, deferredMs);
+            // (a huge HQ_OVERLAP_SLACK forces the maximal deferral whatever it costs: tests of the per-chunk path at sizes
+            // whose exchange is too short to be worth hiding)
+            if (cost < bestCost - 1e-9 || overlapSlack > 1e6) { bestCost = cost; bestFirst = first; }
         }
-        std::vector<GateGroup> prevGroups;
-        if (!overlapSplit) prevGroups = cutGroups(prev, schedule.localGroups[s - 1].state, numLocal, 0);
-        while (!prevGroups.empty()) {
-            const GateGroup& last = prevGroups.back();
-            bool ok = true;
-            for (const Gate& g : last.gates)
-                if (!g.isDiagonal() && !(lowSet >> g.targetQubit & 1)) { ok = false; break; }
-            if (!ok) break;
-            std::vector<GateGroup> recut = cutGroups(last.gates, lg.state, numLocal, exclude);
-            if (recut.size() != 1) break;
-            const double ms = recut[0].predictedMs * (1 << k);   // predictedMs is per chunk
-            if (used + ms > commMs * overlapSlack) break;
-            used += ms;
-            for (const Gate& g : last.gates) ids.push_back(g.gateID);
-            lg.overlapGroups.insert(lg.overlapGroups.begin(), recut[0]);
-            prevGroups.pop_back();
+        if (bestFirst == cand.size()) continue;
+        std::vector<int> ids;
+        for (size_t i = bestFirst; i < cand.size(); i++) {
+            for (auto& g : cand[i].gates) ids.push_back(g.gateID);
+            lg.overlapGroups.push_back(cand[i]);
         }
         std::sort(ids.begin(), ids.end());
         std::vector<Gate> rest;

@@ -26,7 +26,6 @@ public:
     bool enableOverlap; // per-chunk groups under the exchange (reference: ENABLE_OVERLAP)
     int backendMode;   // 1 = tile kernel only, 3 = dense kernel only, 4 = hybrid (reference: -DBACKEND=group|blas|mix)
     int matLimit;      // largest dense block in qubits (reference: -DMAT, BLAS_MAT_LIMIT)
-    bool overlapSplit;  // defer tail GATES (re-cut, may add sweeps) instead of whole trailing groups
     double overlapSlack; // deferred work may take up to this multiple of the predicted exchange time
 private:
     struct Stage { std::vector<Gate> gates; qindex locals; };

@@ -109,6 +109,9 @@ std::unique_ptr<Circuit> parseQasmText(const std::string& text, std::string& err
         if (!c) { err = "gate before qreg"; return nullptr; }
         if ((int)params.size() != spec->params || (int)q.size() != spec->qubits) { err = "wrong operand count for " + head; return nullptr; }
         for (int id : q) if (id < 0 || id >= c->numQubits) { err = "qubit index out of range in " + line; return nullptr; }
+        for (size_t a = 0; a < q.size(); a++)
+            for (size_t b = a + 1; b < q.size(); b++)
+                if (q[a] == q[b]) { err = "repeated qubit in " + line; return nullptr; }
         c->addGate(makeGate(name, q, params));
     }
     if (!c) err = "fail to load circuit";

@@ -36,6 +36,8 @@ int hq_circuit_run(hq_circuit* c, int copy_back, int destroy, int* time_us, doub
 int hq_circuit_prepare_state(hq_circuit* c);
 int hq_circuit_execute(hq_circuit* c, int* time_us, double* device_ms, float* per_group_ms, int cap, int* ngroups);
 int hq_circuit_norm2(hq_circuit* c, double* out);
+/* the schedule's global<->local exchanges alone, back to back (collective; leaves the state permuted) */
+int hq_circuit_swap_alone_ms(hq_circuit* c, double* ms);
 int hq_circuit_io_bytes(const hq_circuit* c, size_t* h2d_plan_bytes, size_t* d2h_dump_bytes);
 int hq_circuit_schedule_info(const hq_circuit* c, int* stages, int* groups, int* gates_in_groups);
 int hq_circuit_group_info(const hq_circuit* c, int index, int* backend, int* ngates, double* predicted_ms, int* launches, int* nblocks);
