@@ -59,6 +59,7 @@ _SIGS = {
     "hq_group_plan_table_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_local_exchanges": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
+    "hq_group_plan_cost": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_double)]),
     "hq_group_plans_warm": (_c.c_int, [_P(_c.c_void_p), _c.c_int]),
     "hq_group_plan_is_specialised": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_jit_available": (_c.c_int, [_P(_c.c_int)]),
@@ -110,8 +111,10 @@ _SIGS = {
     "hq_circuit_io_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_size_t), _P(_c.c_size_t)]),
     "hq_circuit_schedule_info": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),
     "hq_circuit_group_info": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_double), _P(_c.c_int), _P(_c.c_int)]),
+    "hq_circuit_group_cost": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_double)]),
     "hq_circuit_dump": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _P(_c.c_size_t)]),
     "hq_circuit_amplitudes": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_circuit_amp_at": (_c.c_int, [_c.c_void_p, _c.c_longlong, _P(_c.c_double)]),
     "hq_circuit_local_shard": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "hq_circuit_final_layout": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_circuit_logger_flush": (_c.c_int, [_c.c_char_p, _c.c_size_t]),

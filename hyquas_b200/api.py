@@ -134,6 +134,14 @@ class Circuit:
             raise HyquasError(lib.hq_circuit_last_error().decode())
         return out
 
+    def amp_at(self, idx: int) -> complex:
+        """Circuit::ampAt: one amplitude by logical index (every rank must call it when there are several)."""
+        out = (ctypes.c_double * 2)()
+        rc = lib.hq_circuit_amp_at(self._h, int(idx), out)
+        if rc != 0:
+            raise HyquasError(lib.hq_circuit_last_error().decode())
+        return complex(out[0], out[1])
+
     def local_shard(self, world: int) -> np.ndarray:
         """This process' shard (physical order); needs run(destroy=False)."""
         g = world.bit_length() - 1

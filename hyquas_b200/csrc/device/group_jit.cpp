@@ -408,12 +408,12 @@ struct Emitter {
         while (run_bits < K && (plan.tile_mask >> run_bits & 1)) ++run_bits;
         std::vector<std::pair<int, int>> run_dep;   // run number bit -> physical bit
         for (int j = run_bits; j < K; ++j) run_dep.push_back({j - run_bits, tile_phys[j]});
-        char head[2048];
+        char head[2304];
         snprintf(head, sizeof(head),
                  "// generated by hyquas_b200 group_jit: L=%d K=%d rounds=%d ops=%d gates=%d tile_mask=0x%llx\n"
-                 "#define NT %d\n#define TILE %d\n#define NTILES %lluull\n#define NRUNS %d\n#define RUN_AMPS %u\n#define MINB %d\n",
+                 "#define NT %d\n#define TILE %d\n#define NTILES %lluull\n#define NRUNS %d\n#define RUN_AMPS %u\n#define MINB %d\n#define PF_SLOTS %du\n",
                  plan.L, K, plan.nrounds, plan.nops, plan.ngates, (unsigned long long)plan.tile_mask, NT, TILE,
-                 (unsigned long long)P.ntiles, P.nruns, P.run_bytes >> 4, jit_min_blocks(K));
+                 (unsigned long long)P.ntiles, P.nruns, P.run_bytes >> 4, jit_min_blocks(K), jit_l2_prefetch_slots());
         o = head;
         o += "#define HQ_TILE_BASE(t) (" + tile_base_expr() + ")\n";
         o += "#define HQ_RUN_OFF(q) (" + deposit("q", run_dep, true) + ")\n";
@@ -429,6 +429,11 @@ struct Emitter {
 
 }  // namespace
 
+// how many slots ahead of the one being consumed a tile is pulled into L2 (<= 3: off; HQ_JIT_L2_PREFETCH)
+int jit_l2_prefetch_slots() {
+    static const int v = [] { const char* e = getenv("HQ_JIT_L2_PREFETCH"); return e ? std::max(0, std::min(atoi(e), 64)) : 0; }();
+    return v;
+}
 int jit_min_blocks(int K) { return K == 12 ? 1 : (K == 11 ? 2 : 4); }   // CTAs (of two workers, three buffers) per SM
 size_t jit_smem_bytes(int K) { return (size_t)3 * (16u << K) + 64; }
 
@@ -454,13 +459,24 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n"
                  :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* tile, u64* bar, u32 lane) {
+// One tile = NRUNS bulk copies.  The whole worker issues them (thread q copies run q, q + NT, ...): when one warp issued all 128
+// copies of a scattered tile it reached the next barrier a microsecond after the others (r02_s5: 42 gates, 7.75 ms on scattered
+// tiles against 6.4 ms on contiguous ones).  Thread 0 posts the byte count; copies that complete before it did only drive the
+// transaction count negative, the phase cannot complete before the arrive.
+__device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* tile, u64* bar, u32 tid, u32 nthreads) {
     const u64 base = HQ_TILE_BASE(t);
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(TILE * 16) : "memory");
-    __syncwarp();
-    for (u32 q = lane; q < NRUNS; q += 32)
+    if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(TILE * 16) : "memory");
+    for (u32 q = tid; q < NRUNS; q += nthreads)
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      :: "r"(smem_u32(tile + (size_t)q * RUN_AMPS)), "l"(state + base + HQ_RUN_OFF(q)), "r"(RUN_AMPS * 16), "r"(smem_u32(bar)) : "memory");
+}
+// Optional (HQ_JIT_L2_PREFETCH=n > 3, default off): pull the tile n slots ahead into L2.  Shared memory holds three tiles per SM,
+// about what HBM needs in flight (6.5 TB/s x 1.5 us / 148 SMs = 66 KB); measured on supremacy_30 (r02_s4) the prefetch changes
+// nothing (78.7 vs 78.8 ms): the three-buffer rotation already keeps HBM busy.
+__device__ __forceinline__ void prefetch_tile_l2(const double2* state, u64 t, u32 lane) {
+    const u64 base = HQ_TILE_BASE(t);
+    for (u32 q = lane; q < NRUNS; q += 32)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(state + base + HQ_RUN_OFF(q)), "r"(RUN_AMPS * 16) : "memory");
 }
 #define HQ_LD(idx, a, b) { const double2 q_ = tile[idx]; a = q_.x; b = q_.y; }
 #define HQ_ST(idx, a, b) tile[idx] = make_double2(a, b)
@@ -470,7 +486,8 @@ __device__ __forceinline__ void issue_tile_load(double2* state, u64 t, double2* 
 #define HQ_ROUND_DONE()
 // every thread of the worker holds its amplitudes in registers: the buffer can take the tile three slots ahead
 #define HQ_TILE_CONSUMED() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); HQ_SYNC(); \
-        if (s + 3 < nslots && tid < 32) issue_tile_load(state, (u64)blockIdx.x + (u64)(s + 3) * gridDim.x, tile, bar + (s + 3) % 6u, tid); }
+        if (s + 3 < nslots) issue_tile_load(state, (u64)blockIdx.x + (u64)(s + 3) * gridDim.x, tile, bar + (s + 3) % 6u, tid, NT); \
+        if (PF_SLOTS > 3 && s + PF_SLOTS < nslots && tid < 32) prefetch_tile_l2(state, (u64)blockIdx.x + (u64)(s + PF_SLOTS) * gridDim.x, tid); }
 extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2* __restrict__ state) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* bar = reinterpret_cast<u64*>(smem_raw + (size_t)3 * TILE * 16);
@@ -482,9 +499,8 @@ extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x < 32)
-        for (u32 i = 0; i < 3 && i < nslots; ++i)
-            issue_tile_load(state, (u64)blockIdx.x + (u64)i * gridDim.x, reinterpret_cast<double2*>(smem_raw + (size_t)i * TILE * 16), bar + i, threadIdx.x);
+    for (u32 i = 0; i < 3 && i < nslots; ++i)
+        issue_tile_load(state, (u64)blockIdx.x + (u64)i * gridDim.x, reinterpret_cast<double2*>(smem_raw + (size_t)i * TILE * 16), bar + i, threadIdx.x, 2 * NT);
     for (u32 s = wk; s < nslots; s += 2) {
       const u32 b = s % 3u;
       double2* tile = reinterpret_cast<double2*>(smem_raw + (size_t)b * TILE * 16);
@@ -534,7 +550,21 @@ std::string jit_emit_source(const hq_group_plan& plan, bool host) {
     return src;
 }
 
+// FP64 instructions per amplitude of the specialised kernel (what the emitter would write), without keeping the source
+double jit_fp64_per_amp(const hq_group_plan& plan) {
+    Emitter e(plan, false);
+    e.run();
+    return e.ok ? e.stat_fp / (double)R : -1.0;
+}
+
 }  // namespace hq
+
+extern "C" int hq_group_plan_cost(const hq_group_plan* plan, int* rounds, double* fp64_per_amp) {
+    HQ_REQUIRE(plan != nullptr, "null plan");
+    if (rounds) *rounds = plan->nrounds;
+    if (fp64_per_amp) *fp64_per_amp = hq::jit_fp64_per_amp(*plan);
+    return HQ_OK;
+}
 
 extern "C" int hq_debug_group_plan_jit_source(const hq_group_plan* plan, int host_flavour, char* out, size_t cap, size_t* needed) {
     HQ_REQUIRE(plan != nullptr && needed != nullptr, "null argument");

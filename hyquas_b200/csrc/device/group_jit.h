@@ -11,7 +11,9 @@ namespace hq {
 // serial C++ function `hq_group_jit_host(double* state)` with the same arithmetic text (host = true; CPU tests only).
 // Empty string: the emitter does not handle this plan (the interpreter kernel does).
 std::string jit_emit_source(const hq_group_plan& plan, bool host);
+double jit_fp64_per_amp(const hq_group_plan& plan);
 int jit_min_blocks(int K);
+int jit_l2_prefetch_slots();
 size_t jit_smem_bytes(int K);   // dynamic shared memory of the kernel: three tile buffers + mbarriers
 const char* jit_device_prologue();
 const char* jit_device_epilogue();

@@ -774,6 +774,13 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
     }
     // the specialised kernel's source (compiled at the first launch, or for a whole schedule at once by hq_group_plans_warm)
     if (rt().ready && jit_enabled()) plan->jit_source = jit_emit_source(*plan, false);
+    if (const char* dir = getenv("HQ_JIT_DUMP_DIR")) {   // developer aid: keep every emitted source (works without a GPU)
+        static int serial = 0;
+        const std::string src = plan->jit_source.empty() ? jit_emit_source(*plan, false) : plan->jit_source;
+        char name[512];
+        snprintf(name, sizeof(name), "%s/group_%03d.cu", dir, serial++);
+        if (FILE* f = fopen(name, "w")) { fputs(src.c_str(), f); fclose(f); }
+    }
     *out = plan;
     return HQ_OK;
 }

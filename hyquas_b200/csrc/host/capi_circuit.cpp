@@ -149,6 +149,16 @@ extern "C" int hq_circuit_norm2(hq_circuit* h, double* out) {
     return HQ_OK;
 }
 
+// Circuit::ampAt (src/circuit.cpp:95-125): collective when there is more than one process -- every rank must call it
+extern "C" int hq_circuit_amp_at(hq_circuit* h, long long idx, double out_re_im[2]) {
+    if (!h || !out_re_im) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    if (idx < 0 || idx >= (1ll << h->c->numQubits)) { g_cerr = "amplitude index out of range"; return HQ_ERR_ARG; }
+    const ResultItem it = h->c->ampAt(idx);
+    out_re_im[0] = it.amp.x;
+    out_re_im[1] = it.amp.y;
+    return HQ_OK;
+}
+
 extern "C" int hq_circuit_swap_alone_ms(hq_circuit* h, double* ms) {
     if (!h || !ms) { g_cerr = "null argument"; return HQ_ERR_ARG; }
     *ms = h->c->swapAloneMs();
@@ -198,6 +208,24 @@ extern "C" int hq_circuit_group_info(const hq_circuit* h, int index, int* backen
                 return HQ_OK;
             }
     }
+    g_cerr = "group index out of range";
+    return HQ_ERR_ARG;
+}
+
+// Tile-kernel group `index` (execution order, as hq_circuit_group_info): register rounds and FP64 instructions per amplitude of its
+// (first) plan; -1 / -1 for dense groups.
+extern "C" int hq_circuit_group_cost(const hq_circuit* h, int index, int* rounds, double* fp64_per_amp) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    int i = 0;
+    for (const auto& lg : h->c->getSchedule().localGroups)
+        for (const auto* groups : {&lg.overlapGroups, &lg.fullGroups})
+            for (const auto& gg : *groups) {
+                if (i++ != index) continue;
+                if (rounds) *rounds = -1;
+                if (fp64_per_amp) *fp64_per_amp = -1;
+                if (gg.backend != Backend::BLAS && !gg.plans.empty()) return hq_group_plan_cost(static_cast<const hq_group_plan*>(gg.plans[0]), rounds, fp64_per_amp);
+                return HQ_OK;
+            }
     g_cerr = "group index out of range";
     return HQ_ERR_ARG;
 }

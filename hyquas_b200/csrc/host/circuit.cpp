@@ -52,9 +52,9 @@ void Circuit::compile() {
     Executor::release(schedule);
     hyquas::PeepholeStats ph;
     const std::vector<Gate> optimised = hyquas::peephole(gates, &ph);
-    if (ph.zzPatterns + ph.hcxhPatterns + ph.xdxPatterns > 0)
-        Logger::add("Peephole: %d -> %d gates (%d cx-diag-cx, %d h-cx-h, %d x-diag-x patterns made diagonal)", ph.gatesIn, ph.gatesOut,
-                    ph.zzPatterns, ph.hcxhPatterns, ph.xdxPatterns);
+    if (ph.zzPatterns + ph.hcxhPatterns + ph.xdxPatterns + ph.mergedPairs > 0)
+        Logger::add("Peephole: %d -> %d gates (%d cx-diag-cx, %d h-cx-h, %d x-diag-x patterns made diagonal; %d single-qubit pairs merged)",
+                    ph.gatesIn, ph.gatesOut, ph.zzPatterns, ph.hcxhPatterns, ph.xdxPatterns, ph.mergedPairs);
     Compiler compiler(numQubits, optimised);
     schedule = compiler.run();
     int fullGroups = 0, fullGates = 0, overlapGates = 0;

@@ -5,6 +5,8 @@
 #include <complex>
 #include <cstring>
 #include <fstream>
+#include <string>
+#include <vector>
 
 Evaluator* Evaluator::getInstance() {
     static Evaluator* inst = new Evaluator();
@@ -49,7 +51,51 @@ Evaluator::Evaluator() {
     for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
 }
 
-void Evaluator::loadParam(int) {
+// Parameter file in the reference's layout (evaluator-preprocess/process.cpp:167-178, src/evaluator.cpp:60-103), written for
+// this GPU by hq_preprocess: param_type, 14 single-gate + 7 controlled-gate times (us per 512 gates), 10 "K ms" dense lines,
+// one transpose line.  Searched in $HYQUAS_PARAM_DIR, then ../evaluator-preprocess/parameter-files (the reference's path).
+bool Evaluator::loadReferenceLayout(int numQubits) {
+    std::vector<std::string> dirs;
+    if (const char* d = getenv("HYQUAS_PARAM_DIR")) dirs.push_back(d);
+    dirs.push_back("../evaluator-preprocess/parameter-files");
+    for (const std::string& d : dirs) {
+        std::ifstream in(d + "/" + std::to_string(numQubits) + "qubits.out");
+        if (!in) continue;
+        int type = -1;
+        double single[14], ctr[7], dense[10], tr = 0;
+        in >> type;
+        if (type != 1) continue;   // only the partial layout is written / read here
+        for (double& v : single) in >> v;
+        for (double& v : ctr) in >> v;
+        for (double& v : dense) { int K; in >> K >> v; }
+        in >> tr;
+        if (!in) continue;
+        // the default path may hold the REFERENCE's files (its own kernels, possibly another GPU): only files that carry
+        // hq_preprocess's trailing marker are taken from there; an explicit $HYQUAS_PARAM_DIR is trusted as it is
+        std::string marker;
+        in >> marker;
+        if (&d != &dirs[0] || !getenv("HYQUAS_PARAM_DIR")) if (marker != "#hq_preprocess") continue;
+        const double to30 = std::ldexp(1.0, 30 - numQubits) / 1000.0 / 512.0;   // us per 512 gates at 2^L -> ms per gate at 2^30
+        const GateType singles[14] = {GateType::U1, GateType::U2, GateType::U3, GateType::H, GateType::X, GateType::Y, GateType::Z,
+                                      GateType::S, GateType::SDG, GateType::T, GateType::TDG, GateType::RX, GateType::RY, GateType::RZ};
+        const GateType ctrs[7] = {GateType::CNOT, GateType::CY, GateType::CZ, GateType::CRX, GateType::CRY, GateType::CU1, GateType::CRZ};
+        for (int i = 0; i < 14; i++) gateNs[int(singles[i])] = single[i] * to30;
+        for (int i = 0; i < 7; i++) gateNs[int(ctrs[i])] = ctr[i] * to30;
+        gateNs[int(GateType::CCX)] = gateNs[int(GateType::CNOT)];
+        // structural model of the specialised kernels: H = 2 FP64 instructions per amplitude, U3 = 6
+        instrMs30 = std::max(single[3] * to30 / 2.0, single[2] * to30 / 6.0);
+        for (int m = 3; m <= 6; m++) denseMs30[m] = dense[m] * std::ldexp(1.0, 30 - numQubits);
+        for (int m = 0; m < 3; m++) denseMs30[m] = denseMs30[3];
+        return true;
+    }
+    return false;
+}
+
+void Evaluator::loadParam(int numQubits) {
+    if (!triedLayout.count(numQubits)) {
+        triedLayout.insert(numQubits);
+        loadReferenceLayout(numQubits);
+    }
     if (loaded) return;
     loaded = true;
     const char* path = getenv("HYQUAS_PARAM_FILE");

@@ -5,6 +5,7 @@
 // with per-gate-class costs calibrated by the B200 microbenchmarks (tools/calibrate.py writes the parameter
 // file; built-in defaults are the values measured on this pool's B200).
 #pragma once
+#include <set>
 #include <string>
 #include <vector>
 
@@ -28,7 +29,8 @@ public:
     double perfSwap(int numQubits, int k);
     double nvlinkGBs;                       // per-direction bandwidth of one GPU during the exchange
     bool PerGateOrBLAS(const GateGroup* gg_pergate, const GateGroup* gg_blas, int numQubits, int blasSize);
-    void loadParam(int numQubits);          // optional override from $HYQUAS_PARAM_FILE
+    void loadParam(int numQubits);          // optional overrides: {L}qubits.out in the reference's layout (hq_preprocess), $HYQUAS_PARAM_FILE
+    bool loadReferenceLayout(int numQubits);
     // model constants (public so that the calibration tool and tests can read/write them)
     double hbmGBs;                          // achieved sweep bandwidth of the gate-group kernel (read+write)
     double gateNs[32];                      // per-gate cost per 2^30 amplitudes in ms, indexed by GateType
@@ -48,4 +50,5 @@ public:
 private:
     Evaluator();
     bool loaded = false;
+    std::set<int> triedLayout;
 };

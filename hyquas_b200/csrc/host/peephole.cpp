@@ -20,6 +20,7 @@
 //
 // HQ_PEEPHOLE=0 switches the pass off.
 #include "peephole.h"
+#include "evaluator.h"
 
 #include <complex>
 #include <cstdlib>
@@ -180,6 +181,48 @@ std::vector<Gate> peephole(const std::vector<Gate>& in, PeepholeStats* stats) {
             found++;
         }
         st.xdxPatterns += found;
+        if (!found) break;
+        rebuild();
+    }
+
+    // P4: two uncontrolled single-qubit gates on the same qubit with nothing touching that qubit in between become their product
+    // WHEN THAT IS CHEAPER for the specialised tile kernels (Evaluator::instrPerAmp: FP64 instructions per amplitude): u3 ; u3
+    // (12 -> 6, the seams between the SU(4) blocks of a quantum-volume circuit), h ; h (-> identity, dropped), rz ; rz, t ; t
+    // (-> s, free).  A butterfly next to a phase (rx(pi/2) ; t in the supremacy circuits) stays as written: 2 + 1 beats the 6
+    // of a general 2x2.  HQ_PEEPHOLE_MERGE=0 switches it off.
+    const bool mergePass = !(getenv("HQ_PEEPHOLE_MERGE") && atoi(getenv("HQ_PEEPHOLE_MERGE")) == 0);
+    for (int sweep = 0; sweep < 64 && mergePass; sweep++) {
+        int found = 0;
+        auto plain = [](const Gate& q) { return q.controlQubit == -1 && q.controlQubit2 == -1 && q.targetQubit >= 0; };
+        for (size_t i = 0; i < g.size(); i++) {
+            if (dead[i] || !plain(g[i])) continue;
+            const int a = g[i].targetQubit;
+            const int j = nextTouching(g, dead, i, a, -1);
+            if (j < 0 || !plain(g[j])) continue;
+            Cx A[2][2], B[2][2], P[2][2];
+            for (int r = 0; r < 2; r++)
+                for (int c = 0; c < 2; c++) { A[r][c] = Cx(g[i].mat[r][c].x, g[i].mat[r][c].y); B[r][c] = Cx(g[j].mat[r][c].x, g[j].mat[r][c].y); }
+            for (int r = 0; r < 2; r++)
+                for (int c = 0; c < 2; c++) {
+                    P[r][c] = B[r][0] * A[0][c] + B[r][1] * A[1][c];   // second gate times first
+                    // exact zeros where the factors say so (h ; h must give the identity, not 1e-17 off-diagonals)
+                    if (std::abs(P[r][c]) < 4e-16) P[r][c] = 0;
+                    if (std::abs(P[r][c].real()) < 4e-16 * std::abs(P[r][c])) P[r][c] = Cx(0, P[r][c].imag());
+                    if (std::abs(P[r][c].imag()) < 4e-16 * std::abs(P[r][c])) P[r][c] = Cx(P[r][c].real(), 0);
+                    if (std::abs(std::abs(P[r][c].real()) - 1.0) < 4e-16 && P[r][c].imag() == 0) P[r][c] = Cx(P[r][c].real() > 0 ? 1 : -1, 0);
+                    if (std::abs(std::abs(P[r][c].imag()) - 1.0) < 4e-16 && P[r][c].real() == 0) P[r][c] = Cx(0, P[r][c].imag() > 0 ? 1 : -1);
+                }
+            const qComplex m[4] = {make_cuDoubleComplex(P[0][0].real(), P[0][0].imag()), make_cuDoubleComplex(P[0][1].real(), P[0][1].imag()),
+                                   make_cuDoubleComplex(P[1][0].real(), P[1][0].imag()), make_cuDoubleComplex(P[1][1].real(), P[1][1].imag())};
+            const bool diag = P[0][1] == Cx(0, 0) && P[1][0] == Cx(0, 0);
+            Gate merged = diag ? Gate::make(GateType::RZ, "RZ", -1, -1, a, m) : Gate::make(GateType::U3, "U3", -1, -1, a, m);
+            if (Evaluator::instrPerAmp(merged) + 1e-9 >= Evaluator::instrPerAmp(g[i]) + Evaluator::instrPerAmp(g[j])) continue;
+            const bool identity = diag && P[0][0] == Cx(1, 0) && P[1][1] == Cx(1, 0);
+            dead[i] = 1;
+            if (identity) dead[j] = 1; else g[j] = merged;   // the product sits where the second gate was
+            found++;
+        }
+        st.mergedPairs += found;
         if (!found) break;
         rebuild();
     }

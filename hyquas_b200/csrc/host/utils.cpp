@@ -4,9 +4,21 @@
 // the reference's USE_MPI layout with one GPU per rank (src/utils.cpp:17-74); without them numGPUs = 1.
 #include "utils.h"
 
+#include <signal.h>
+#include <spawn.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iterator>
+#include <vector>
 #include "logger.h"
 #include "swap.h"
+
+extern char** environ;
 
 namespace MyGlobalVars {
 int numGPUs = 1;
@@ -20,7 +32,96 @@ static int envInt(const char* key, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// Launcher mode.  The reference's single-process build drives every visible GPU from one `./main file.qasm`
+// (src/utils.cpp:17-60); here one process drives one GPU, so a native program started WITHOUT a launcher environment
+// (no RANK / WORLD_SIZE) on a box with several GPUs re-executes itself once per GPU -- RANK, LOCAL_RANK, WORLD_SIZE, MASTER_PORT
+// set -- waits for the ranks and exits with their status: scripts/check_wrapper.sh style drivers work unchanged.  The GPU count is
+// taken from a throw-away child so that this process never initialises CUDA.  HQ_NUM_GPUS=n picks the count (1: stay single),
+// HQ_SELF_SPAWN=0 switches the mode off; interpreters (python) never self-spawn -- they are launched by torchrun.
+static void selfSpawnIfNeeded() {
+    if (getenv("RANK") || getenv("WORLD_SIZE") || getenv("HQ_SPAWNED")) return;
+    if (const char* e = getenv("HQ_SELF_SPAWN")) if (atoi(e) == 0) return;
+    char exe[4096];
+    const ssize_t len = readlink("/proc/self/exe", exe, sizeof(exe) - 1);
+    if (len <= 0) return;
+    exe[len] = 0;
+    const char* base = strrchr(exe, '/');
+    if (strstr(base ? base : exe, "python")) return;
+    int want = envInt("HQ_NUM_GPUS", 0);
+    if (want == 1) return;
+    std::vector<std::string> args;
+    {
+        std::ifstream in("/proc/self/cmdline", std::ios::binary);
+        std::string all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        size_t pos = 0;
+        while (pos < all.size()) { args.push_back(all.c_str() + pos); pos += args.back().size() + 1; }
+    }
+    if (args.empty()) return;
+    auto spawn = [&](const std::vector<std::string>& extraEnv, int outFd) {
+        std::vector<char*> argv;
+        for (auto& a : args) argv.push_back(const_cast<char*>(a.c_str()));
+        argv.push_back(nullptr);
+        std::vector<std::string> envs;
+        for (char** e = environ; *e; e++) envs.push_back(*e);
+        for (auto& e : extraEnv) envs.push_back(e);
+        std::vector<char*> envp;
+        for (auto& e : envs) envp.push_back(const_cast<char*>(e.c_str()));
+        envp.push_back(nullptr);
+        posix_spawn_file_actions_t fa;
+        posix_spawn_file_actions_init(&fa);
+        if (outFd >= 0) posix_spawn_file_actions_adddup2(&fa, outFd, 1);
+        pid_t pid = -1;
+        const int rc = posix_spawn(&pid, exe, &fa, nullptr, argv.data(), envp.data());
+        posix_spawn_file_actions_destroy(&fa);
+        return rc == 0 ? pid : (pid_t)-1;
+    };
+    int visible = 0;
+    {   // GPU count from a child (HQ_COUNT_GPUS): CUDA stays uninitialised here
+        int fds[2];
+        if (pipe(fds) != 0) return;
+        const pid_t pid = spawn({"HQ_COUNT_GPUS=1", "HQ_SPAWNED=1"}, fds[1]);
+        close(fds[1]);
+        if (pid < 0) { close(fds[0]); return; }
+        char buf[64] = {0};
+        const ssize_t n = read(fds[0], buf, sizeof(buf) - 1);
+        close(fds[0]);
+        int st = 0;
+        waitpid(pid, &st, 0);
+        if (n > 0) visible = atoi(buf);
+    }
+    int n = 1;
+    while (n * 2 <= visible) n *= 2;
+    if (want > 1) { int w = 1; while (w * 2 <= want) w *= 2; n = std::min(n, w); }
+    if (n <= 1) return;
+    const std::string port = "MASTER_PORT=" + std::to_string(20000 + (int)(getpid() % 20000));
+    const std::string run = "TORCHELASTIC_RUN_ID=hq" + std::to_string((long long)time(nullptr));
+    std::vector<pid_t> kids;
+    for (int r = 0; r < n; r++) {
+        const pid_t pid = spawn({"RANK=" + std::to_string(r), "LOCAL_RANK=" + std::to_string(r), "WORLD_SIZE=" + std::to_string(n),
+                                 "HQ_SPAWNED=1", port, run, "MASTER_ADDR=127.0.0.1"}, -1);
+        if (pid < 0) { fprintf(stderr, "hyquas_b200: cannot start rank %d\n", r); for (pid_t k : kids) kill(k, SIGTERM); exit(1); }
+        kids.push_back(pid);
+    }
+    int worst = 0;
+    for (pid_t k : kids) {
+        int st = 0;
+        waitpid(k, &st, 0);
+        const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + (WIFSIGNALED(st) ? WTERMSIG(st) : 0);
+        if (code != 0 && worst == 0) { worst = code; for (pid_t o : kids) if (o != k) kill(o, SIGTERM); }
+    }
+    fflush(stdout);
+    _exit(worst);
+}
+
 void init() {
+    if (getenv("HQ_COUNT_GPUS")) {   // the launcher's throw-away child: print the device count and leave
+        int visible = 0;
+        if (hq_device_count(&visible) != HQ_OK) visible = 0;
+        printf("%d\n", visible);
+        fflush(stdout);
+        _exit(0);
+    }
+    selfSpawnIfNeeded();
     MyMPI::init();
     numGPUs = MyMPI::commSize;
     localGPUs = 1;

@@ -91,6 +91,8 @@ int hq_group_plan_destroy(hq_group_plan* plan);
 /* Gate groups run as per-group specialised kernels (NVRTC, sm_100a; cached in memory and under $HQ_JIT_CACHE or
  * ~/.cache/hyquas_b200/jit; HQ_JIT=0 keeps the interpreter kernel).  A plan compiles at its first launch; warming a whole
  * schedule's plans at once compiles the cache misses on all host cores. */
+/* what the specialised kernel of this plan costs: register rounds and FP64 instructions per amplitude (works host-only) */
+int hq_group_plan_cost(const hq_group_plan* plan, int* rounds, double* fp64_per_amp);
 int hq_group_plans_warm(hq_group_plan* const* plans, int n);
 int hq_group_plan_is_specialised(const hq_group_plan* plan, int* yes);
 int hq_jit_available(int* yes);   /* HQ_JIT not 0 and NVRTC loadable; the evaluator prices tile groups accordingly */

@@ -41,8 +41,10 @@ int hq_circuit_swap_alone_ms(hq_circuit* c, double* ms);
 int hq_circuit_io_bytes(const hq_circuit* c, size_t* h2d_plan_bytes, size_t* d2h_dump_bytes);
 int hq_circuit_schedule_info(const hq_circuit* c, int* stages, int* groups, int* gates_in_groups);
 int hq_circuit_group_info(const hq_circuit* c, int index, int* backend, int* ngates, double* predicted_ms, int* launches, int* nblocks);
+int hq_circuit_group_cost(const hq_circuit* c, int index, int* rounds, double* fp64_per_amp);   /* tile groups: rounds, FP64 instr / amplitude */
 int hq_circuit_dump(hq_circuit* c, char* buf, size_t cap, size_t* needed);              /* printState text */
 int hq_circuit_amplitudes(hq_circuit* c, double* out_re_im); /* all 2^n amplitudes, logical order (small n) */
+int hq_circuit_amp_at(hq_circuit* c, long long idx, double out_re_im[2]);   /* Circuit::ampAt; collective across processes */
 int hq_circuit_local_shard(hq_circuit* c, double* out_re_im);  /* this process' 2^(n-g) amplitudes, physical order */
 int hq_circuit_final_layout(hq_circuit* c, int* pos);         /* pos[logical qubit] = physical bit (Schedule::finalState) */
 int hq_circuit_logger_flush(char* buf, size_t cap);          /* Logger::print */

@@ -73,3 +73,40 @@ def test_reference_sources_compile_against_our_headers():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     for name in ("main", "local-single", "local-ctr", "two-group-h", "bench-blas"):
         assert os.path.exists(os.path.join(root, "oracle", "_ref", "dropin_" + name))
+
+
+def test_add_gate_rejects_bad_operands():
+    """Operands must be in range and distinct, controlled types need their controls: an error code, not a dead process."""
+    from hyquas_b200 import api
+    from hyquas_b200._lib import HyquasError
+    c = api.Circuit(5)
+    c.add_gate("CNOT", 0, 1)
+    for bad in [("CNOT", (1, 1)), ("CCX", (0, 0, 2)), ("CCX", (0, 1, 1)), ("H", (7,)), ("CZ", (2, 9))]:
+        with pytest.raises(HyquasError):
+            c.add_gate(bad[0], *bad[1])
+    import ctypes
+    from hyquas_b200._lib import lib
+    arr = (ctypes.c_double * 1)(0.0)
+    assert lib.hq_circuit_add_gate(c._h, 1, -1, -1, 2, arr, 0) != 0     # CNOT without a control
+    assert lib.hq_circuit_add_gate(c._h, 11, -1, 3, 2, arr, 0) != 0     # H with a control
+    assert c.num_gates == 1
+    with pytest.raises(HyquasError):
+        api.Circuit.from_qasm('OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[4];\ncx q[1],q[1];\n')
+
+
+def test_compile_refuses_too_few_local_qubits_with_an_error_code():
+    """12 qubits on 8 GPUs leave 9 local qubits: the tile kernel needs 10; compile() must say so, not exit."""
+    import subprocess
+    import sys
+    code = ("from hyquas_b200 import api, circuits\n"
+            "from hyquas_b200._lib import HyquasError\n"
+            "api.init_host_only(8, 0)\n"
+            "c = api.Circuit.from_qasm(circuits.random_circuit(12, 60, 1))\n"
+            "try:\n    c.compile()\nexcept HyquasError as e:\n    print('refused:', e)\n"
+            "try:\n    c.plan_only()\nexcept HyquasError as e:\n    print('refused plan:', e)\n"
+            "api.init_host_only(8, 0)\n"
+            "c2 = api.Circuit.from_qasm(circuits.random_circuit(13, 60, 1)); print(c2.plan_only())\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert "refused:" in r.stdout and "refused plan:" in r.stdout and "at least 10 are needed" in r.stdout
+    assert "'stages'" in r.stdout

@@ -116,7 +116,8 @@ def test_reference_goldens_byte_exact(gpu_runtime, golden_dir, name):
 
 
 @pytest.mark.parametrize("name,backend", [("supremacy_26", "b1"), ("quantum_volume_24", "b3"), ("qaoa_26", "b1"),
-                                          ("basis_change_24", "b3"), ("supremacy_28", "b3")])
+                                          ("basis_change_24", "b3"), ("supremacy_28", "b3"),
+                                          ("supremacy_30", "b1"), ("quantum_volume_30", "b3")])   # BASELINE sizes (16 GiB state)
 def test_same_dump_as_reference_build(gpu_runtime, tmp_path, name, backend):
     """Families whose upstream goldens are lost: our printState text vs the text printed by the reference's
     OWN binary (oracle/_ref/hyquas_ref_b1 = OShareMem build, b3 = TransMM build, compiled from /root/reference by
@@ -129,7 +130,8 @@ def test_same_dump_as_reference_build(gpu_runtime, tmp_path, name, backend):
     text = C.generate(name)
     qasm = tmp_path / (name + ".qasm")
     qasm.write_text(text)
-    r = subprocess.run([exe, str(qasm)], capture_output=True, text=True, timeout=300)
+    # one GPU for the reference too (it drives every visible GPU otherwise, src/utils.cpp:17-60)
+    r = subprocess.run([exe, str(qasm)], capture_output=True, text=True, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES="0"))
     assert r.returncode == 0, r.stderr[-500:]
     ref_dump = "".join(l + "\n" for l in r.stdout.splitlines() if re.match(r"^\d+ \d\.\d+: ", l))
     assert ref_dump.count("\n") >= 128

@@ -11,6 +11,13 @@ from hyquas_b200._lib import check, lib
 from oracle import oracle as O
 
 
+@pytest.fixture(autouse=True)
+def _count_gates_without_the_merge_pass(monkeypatch, request):
+    """The pattern tests below count gates in and out; the single-qubit merge pass (P4) has its own tests at the end."""
+    if "merge" not in request.node.name:
+        monkeypatch.setenv("HQ_PEEPHOLE_MERGE", "0")
+
+
 def run(text):
     api.init_host_only(1, 0)
     c = api.Circuit.from_qasm(text)
@@ -152,3 +159,25 @@ def test_random_pattern_rich_circuits(seed, monkeypatch):
             lines.append(f"ry({rng.uniform(0.1, 3.0):.6f}) q[{a}];")
     got, want, _, _ = run(qasm(n, lines))
     assert np.max(np.abs(got - want)) < 1e-12
+
+
+def test_merge_pass_multiplies_adjacent_single_qubit_gates_when_cheaper():
+    """u3 ; u3 -> one gate, h ; h -> nothing, t ; t -> one phase; rx(pi/2) ; t stays (a butterfly and a phase cost 3 FP64
+    instructions per amplitude, their product 6); a cx in between blocks the merge.  Amplitudes as the oracle's."""
+    lines = PREP + ["u3(0.3,0.1,0.2) q[0];", "u3(1.3,0.4,0.7) q[0];",        # -> 1
+                    "h q[1];", "h q[1];",                                    # -> 0
+                    "t q[2];", "t q[2];",                                    # -> 1
+                    "rx(pi/2) q[3];", "t q[3];",                             # stays 2
+                    "u3(0.3,0.1,0.2) q[5];", "cx q[5],q[6];", "u3(1.3,0.4,0.7) q[5];",   # stays 3
+                    "rz(0.4) q[7];", "rz(0.9) q[7];", "rz(1.9) q[7];"]       # -> 1
+    got, want, info, ngates = run(qasm(10, lines))
+    assert np.max(np.abs(got - want)) < 1e-12
+    # PREP's own gates merge with what follows them on qubits 0 (h;u3;u3 -> 1), 1 (ry;h;h -> ry), 2 and 7 (rx ; phases: no)
+    assert info["gates"] < ngates - 5
+
+
+def test_merge_pass_on_quantum_volume_matches_oracle():
+    text = C.quantum_volume(12, depth=6, seed=3)
+    got, want, info, ngates = run(text)
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert info["gates"] < ngates

@@ -100,6 +100,7 @@ def main():
         "h_x256_4q": (["H"], 256, hi4),
     }
     os.environ["HQ_BACKEND"] = "group"      # these cases price the TILE kernel; the hybrid partitioner would fuse them
+    os.environ["HQ_PEEPHOLE_MERGE"] = "0"   # ... and the merge pass would multiply the repeated gates together
     cases.update({
         "h_x96_12q_hi": (["H"], 96, list(range(16, 28))),     # same, on qubits the partitioner is free to place
         "t_x96_12q": (["T"], 96, list(range(12))),
@@ -107,6 +108,13 @@ def main():
         "sup5_x96_12q": (["H", "RXH", "T", "RYH", "CZ"], 96, list(range(12))),
         "mix5_x256_12q": (["H", "RX", "T", "RY", "CZ"], 256, list(range(12))),
     })
+    # tile geometry: the same light / medium work on tiles made of the 5 pinned low bits + 7 qubits at different heights
+    # (contiguous 64 KB tile ... 128 runs of 512 B spread over the whole state)
+    for tag, qs in (("lo7", list(range(5, 12))), ("mid7", list(range(12, 19))), ("hi7", list(range(n - 8, n - 1))),
+                    ("spread7", [6, 9, 13, 17, 21, 25, n - 1])):
+        cases["sweep_" + tag] = (["H"], 7, qs)
+        cases["sup5_x42_" + tag] = (["H", "RXH", "T", "RYH", "CZ"], 42, qs)
+        cases["sup5_x84_" + tag] = (["H", "RXH", "T", "RYH", "CZ"], 84, qs)
     for name, (spec, count, qubits) in cases.items():
         if only and name not in only:
             continue
