@@ -132,6 +132,8 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
         const std::string v = e;
         if (v == "off") enableOverlap = false;
     }
+    rebalanceGroups = true;
+    if (const char* e = getenv("HQ_REBALANCE")) rebalanceGroups = atoi(e) != 0;
     cutBothWays = true;
     if (const char* e = getenv("HQ_CUT_BOTH_WAYS")) cutBothWays = atoi(e) != 0;
     maxGroupGates = 384;
@@ -288,7 +290,83 @@ GateGroup Compiler::denseCandidate(const std::vector<Gate>& stageGates, const st
 // the reversed list, reversed, is a valid cut of the list); the cheaper predicted total wins.  The front-to-back cut leaves
 // its crumbs (launches with a handful of gates, a full sweep each) at the end of the stage, the other one at the start, and
 // which of the two is smaller depends on the circuit.
+// A tile-kernel launch costs max(sweep, arithmetic + exchanges): the greedy cut fills every group to the brim, which leaves some
+// launches compute-bound (11 ms) next to sweep-bound ones with arithmetic to spare (5.5 ms).  Adjacent tile groups may trade
+// gates without changing what is computed: a suffix-closed set of group i whose non-diagonal targets lie in group i+1's tile can
+// open group i+1 instead, and a prefix-closed set of group i+1 that fits group i's tile can close group i.  Greedy descent on the
+// predicted total, pair by pair; a group that ends up empty disappears (that is how trailing crumbs are absorbed).
+void Compiler::rebalance(std::vector<GateGroup>& groups, int nEff) const {
+    if (!rebalanceGroups || groups.size() < 2) return;
+    Evaluator* ev = Evaluator::getInstance();
+    auto cost = [&](const std::vector<Gate>& g) { return g.empty() ? 0.0 : ev->perfPerGate(nEff, g); };
+    for (int pass = 0; pass < 4; pass++) {
+        bool changed = false;
+        for (size_t i = 0; i + 1 < groups.size(); i++) {
+            GateGroup &A = groups[i], &B = groups[i + 1];
+            if (A.backend != Backend::PerGate || B.backend != Backend::PerGate) continue;
+            const double base = cost(A.gates) + cost(B.gates);
+            double best = base - 0.05;   // a move must win at least 50 us
+            int bestDir = 0;
+            size_t bestK = 0;
+            // direction +1: the tail of A opens B
+            std::vector<int> order(A.gates.size());
+            for (size_t j = 0; j < order.size(); j++) order[j] = (int)A.gates.size() - 1 - (int)j;
+            const std::vector<int> tail = hyquas::runnableGates(A.gates, order, B.relatedQubits, 1 << 30);   // nearest the end first
+            // direction -1: the head of B closes A
+            std::vector<int> fwdOrder(B.gates.size());
+            for (size_t j = 0; j < fwdOrder.size(); j++) fwdOrder[j] = (int)j;
+            const std::vector<int> head = hyquas::runnableGates(B.gates, fwdOrder, A.relatedQubits, 1 << 30);
+            auto split = [&](const std::vector<Gate>& src, const std::vector<int>& picked, size_t k, std::vector<Gate>& keep, std::vector<Gate>& moved) {
+                std::vector<char> take(src.size(), 0);
+                for (size_t j = 0; j < k; j++) take[picked[j]] = 1;
+                keep.clear(); moved.clear();
+                for (size_t j = 0; j < src.size(); j++) (take[j] ? moved : keep).push_back(src[j]);
+            };
+            std::vector<Gate> keep, moved, other;
+            for (int dir : {+1, -1}) {
+                const std::vector<int>& picked = dir > 0 ? tail : head;
+                const std::vector<Gate>& src = dir > 0 ? A.gates : B.gates;
+                const std::vector<Gate>& dst = dir > 0 ? B.gates : A.gates;
+                // try a handful of sizes (every 4th gate, plus everything: emptying a group removes a whole sweep)
+                for (size_t k = 1; k <= picked.size(); k = (k + 4 <= picked.size() || k == picked.size()) ? k + 4 : picked.size()) {
+                    if ((int)(dst.size() + k) > maxGroupGates) break;
+                    split(src, picked, k, keep, moved);
+                    if (dir > 0) { other = moved; other.insert(other.end(), dst.begin(), dst.end()); }
+                    else { other = dst; other.insert(other.end(), moved.begin(), moved.end()); }
+                    const double c = cost(keep) + cost(other);
+                    if (c < best) { best = c; bestDir = dir; bestK = k; }
+                    if (k == picked.size()) break;
+                }
+            }
+            if (!bestDir) continue;
+            const std::vector<int>& picked = bestDir > 0 ? tail : head;
+            if (bestDir > 0) {
+                split(A.gates, picked, bestK, keep, moved);
+                A.gates = keep;
+                moved.insert(moved.end(), B.gates.begin(), B.gates.end());
+                B.gates = moved;
+            } else {
+                split(B.gates, picked, bestK, keep, moved);
+                B.gates = keep;
+                A.gates.insert(A.gates.end(), moved.begin(), moved.end());
+            }
+            A.predictedMs = cost(A.gates);
+            B.predictedMs = cost(B.gates);
+            changed = true;
+        }
+        for (size_t i = groups.size(); i-- > 0;)
+            if (groups[i].backend == Backend::PerGate && groups[i].gates.empty()) groups.erase(groups.begin() + i);
+        if (!changed) break;
+    }
+}
+
 std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal, qindex exclude) const {
+    std::vector<GateGroup> out = cutGroupsBothWays(stageGates, state, nLocal, exclude);
+    rebalance(out, nLocal - bitCount(exclude));
+    return out;
+}
+
+std::vector<GateGroup> Compiler::cutGroupsBothWays(const std::vector<Gate>& stageGates, const State& state, int nLocal, qindex exclude) const {
     std::vector<GateGroup> fwd = cutGroupsGreedy(stageGates, state, nLocal, exclude);
     // (only for stages of <= 256 gates: there the second cut costs about a millisecond of compile time and removes a sweep
     // from bv / adder; on the long random circuits it never won and would only add 15-60 ms to compile())

@@ -22,6 +22,7 @@ public:
     int tileBits;      // qubits per tile of the gate-group kernel
     int pinnedBits;    // lowest physical bits always kept in the tile (contiguous-run length of HBM accesses)
     int maxGroupGates; // cap on gates per group
+    bool rebalanceGroups; // adjacent tile groups trade gates to even out compute-bound and sweep-bound launches (HQ_REBALANCE)
     bool cutBothWays;  // try the greedy cut from both ends of a stage, keep the cheaper predicted total
     bool enableOverlap; // per-chunk groups under the exchange (reference: ENABLE_OVERLAP)
     int backendMode;   // 1 = tile kernel only, 3 = dense kernel only, 4 = hybrid (reference: -DBACKEND=group|blas|mix)
@@ -32,6 +33,8 @@ private:
     std::vector<Stage> splitStages() const;
     GateGroup denseCandidate(const std::vector<Gate>& gates, const std::vector<int>& remaining, const State& state, int numLocal, qindex exclude) const;
     std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
+    std::vector<GateGroup> cutGroupsBothWays(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
+    void rebalance(std::vector<GateGroup>& groups, int nEff) const;
     std::vector<GateGroup> cutGroupsGreedy(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     int numQubits;
     int numLocal;

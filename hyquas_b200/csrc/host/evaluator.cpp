@@ -44,8 +44,8 @@ Evaluator::Evaluator() {
     int avail = 0;
     hq_jit_available(&avail);
     specialised = avail != 0;
-    instrMs30 = 0.066;
-    jitRoundMs30 = 0.4;
+    instrMs30 = 0.060;      // h_x256_4q: 512 instructions per amplitude in 30.8 ms
+    jitRoundMs30 = 0.9;     // supremacy_30 launches: 112-124 instructions per amplitude in 3-5 rounds take 9.6-11.6 ms
     jitBaseMs30 = 0.3;
     const double dense[8] = {2.75, 2.75, 2.75, 2.75, 5.0, 9.7, 18.3, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
     for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
@@ -184,18 +184,46 @@ double Evaluator::instrPerAmp(const Gate& g) {
     return cost;
 }
 
-// With the gates at hand the number of register rounds can be bounded from below: a round holds 4 register qubits.
+// Register rounds the tile kernel's planner will need (device/group_kernel.cu: a round holds 4 register qubits; a gate joins the
+// current round when nothing it fails to commute with was left behind and its non-diagonal target is, or can still become, a
+// register qubit): the same greedy fill, on logical qubits.
+int Evaluator::registerRounds(const std::vector<Gate>& gates) {
+    std::vector<char> done(gates.size(), 0);
+    size_t left = gates.size();
+    int rounds = 0;
+    while (left > 0) {
+        qindex blockedX = 0, blockedZ = 0, reg = 0;
+        int nreg = 0;
+        for (size_t i = 0; i < gates.size(); i++) {
+            if (done[i]) continue;
+            const Gate& g = gates[i];
+            const bool diag = g.isDiagonal();
+            qindex qn = 0, qd = 0;
+            (diag ? qd : qn) |= qindex(1) << g.targetQubit;
+            if (g.controlQubit >= 0) qd |= qindex(1) << g.controlQubit;
+            if (g.controlQubit2 >= 0) qd |= qindex(1) << g.controlQubit2;
+            bool can = !(qn & (blockedX | blockedZ)) && !(qd & blockedX);
+            if (can && !diag && !(reg >> g.targetQubit & 1)) {
+                if (nreg < 4) { reg |= qindex(1) << g.targetQubit; nreg++; }
+                else can = false;
+            }
+            if (can) { done[i] = 1; left--; }
+            else { blockedX |= qn; blockedZ |= qd; }
+        }
+        rounds++;
+    }
+    return std::max(1, rounds);
+}
+
 double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
     loadParam(numQubits);
     if (specialised) {
         double instr = 0;
-        qindex targets = 0;
-        for (const Gate& g : gates) {
-            instr += instrPerAmp(g);
-            if (!g.isDiagonal()) targets |= qindex(1) << g.targetQubit;
-        }
-        const int rounds = std::max(1, (bitCount(targets) + 3) / 4);
-        const double compute = jitBaseMs30 + instrMs30 * instr + jitRoundMs30 * (rounds - 1);
+        for (const Gate& g : gates) instr += instrPerAmp(g);
+        const int rounds = registerRounds(gates);
+        // every round after the first moves the tile through shared memory once more (64 KB out, 64 KB in per tile: 0.9 ms per
+        // 2^30 amplitudes at 128 B/clk/SM) and flushes the pending coefficients (<= 2 instructions per amplitude)
+        const double compute = jitBaseMs30 + instrMs30 * (instr + 2.0 * rounds) + jitRoundMs30 * (rounds - 1);
         return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
     }
     double compute = groupBaseMs30;

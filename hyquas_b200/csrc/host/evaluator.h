@@ -47,6 +47,7 @@ public:
     double jitRoundMs30;                    // coefficient flush + shared-memory exchange of one extra round
     double jitBaseMs30;
     static double instrPerAmp(const Gate& g);
+    static int registerRounds(const std::vector<Gate>& gates);   // rounds the tile kernel will need for this group
 private:
     Evaluator();
     bool loaded = false;
