@@ -441,6 +441,7 @@ def run_ours(args, world, rank, local_rank):
     # ---- how much of the exchange is hidden (N > 1): same circuit with the per-chunk overlap groups switched off -------------
     overlap = None
     if world > 1 and not args.no_overlap_probe:
+        c.release_state()           # one state at a time; the p2p mapping follows the live state
         os.environ["HQ_ENABLE_OVERLAP"] = "0"
         c2 = api.Circuit.from_qasm(text)
         c2.compile()
@@ -457,14 +458,17 @@ def run_ours(args, world, rank, local_rank):
         t = torch.tensor([off_ms / reps], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         off_ms = float(t.item())
-        c2.close()
         sw = ctypes.c_double()
-        check(lib.hq_circuit_swap_alone_ms(c._h, sw))
+        check(lib.hq_circuit_swap_alone_ms(c2._h, sw))   # warm-up pass
+        barrier()
+        check(lib.hq_circuit_swap_alone_ms(c2._h, sw))
         t = torch.tensor([sw.value], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         swap_ms = float(t.item())
+        off_sweeps = c2.schedule_info()["groups"]
+        c2.close()
         overlap = {"overlap_groups": sum(1 for gi in ginfo if gi["launches"] > 1), "time_overlap_on_ms": ms_per_step,
-                   "time_overlap_off_ms": off_ms, "swap_alone_ms": swap_ms,
+                   "time_overlap_off_ms": off_ms, "sweeps_overlap_off": off_sweeps, "swap_alone_ms": swap_ms,
                    "hidden_frac": (off_ms - ms_per_step) / swap_ms if swap_ms > 0 else None,
                    "definition": "(T_overlap_off - T_overlap_on) / T_swap_alone; swap_alone = the schedule's exchanges run back to back with no compute"}
     c.close()

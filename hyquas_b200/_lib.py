@@ -49,6 +49,7 @@ _SIGS = {
     "hq_state_upload": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p]),
     "hq_amp_fetch": (_c.c_int, [_c.c_void_p, _c.c_int64, _P(_c.c_double)]),
     "hq_dump_scan": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_int64, _P(_c.c_int64)]),
+    "hq_state_measure": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_double)]),
     "hq_state_norm2": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
     "hq_group_tile_bits": (_c.c_int, []),
     "hq_group_min_run_bits": (_c.c_int, []),
@@ -106,6 +107,8 @@ _SIGS = {
     "hq_circuit_run": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _P(_c.c_int), _P(_c.c_double)]),
     "hq_circuit_prepare_state": (_c.c_int, [_c.c_void_p]),
     "hq_circuit_execute": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_double), _P(_c.c_float), _c.c_int, _P(_c.c_int)]),
+    "hq_circuit_measure": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_double)]),
+    "hq_circuit_release_state": (_c.c_int, [_c.c_void_p]),
     "hq_circuit_norm2": (_c.c_int, [_c.c_void_p, _P(_c.c_double)]),
     "hq_circuit_swap_alone_ms": (_c.c_int, [_c.c_void_p, _P(_c.c_double)]),
     "hq_circuit_io_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_size_t), _P(_c.c_size_t)]),

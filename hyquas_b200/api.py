@@ -109,9 +109,19 @@ class Circuit:
         check(lib.hq_circuit_execute(self._h, us, ms, None, 0, n))
         return us.value, ms.value
 
+    def release_state(self) -> None:
+        """Free the resident state vector; the compiled schedule stays (prepare_state() allocates again)."""
+        check(lib.hq_circuit_release_state(self._h))
+
     def norm2(self) -> float:
         v = ctypes.c_double()
         check(lib.hq_circuit_norm2(self._h, v))
+        return v.value
+
+    def measure(self, qubit: int) -> float:
+        """Probability that the logical qubit reads 0 (every rank must call it when there are several)."""
+        v = ctypes.c_double()
+        check(lib.hq_circuit_measure(self._h, int(qubit), v))
         return v.value
 
     def io_bytes(self):

@@ -63,6 +63,54 @@ __global__ void norm2_kernel(const double2* s, uint64_t n, double* out) {
     }
 }
 
+// P(target bit = 0) = sum |a|^2 over the amplitudes whose physical index has bit t clear (kernelMeasure / measure<>,
+// src/kernelSimple.cu:482-516 of the reference).  Only that half of the state is read: index i of 2^(L-1) maps to
+// lo = ((i >> t) << (t + 1)) | (i & (2^t - 1)); four independent loads in flight per thread, per-block partial sums written to
+// `partial` (a fixed-order second pass adds them, so the result does not depend on atomics ordering).
+__global__ void measure_kernel(const double2* __restrict__ s, uint64_t half, int t, double* __restrict__ partial) {
+    __shared__ double red[32];
+    const uint64_t lowmask = (1ull << t) - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < half; i += 4 * stride) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t j = i + (uint64_t)u * stride;
+            v[u] = s[((j >> t) << (t + 1)) | (j & lowmask)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(v[u].x, v[u].x, fma(v[u].y, v[u].y, acc[u]));
+    }
+    for (; i < half; i += stride) {
+        const double2 v = s[((i >> t) << (t + 1)) | (i & lowmask)];
+        acc[0] = fma(v.x, v.x, fma(v.y, v.y, acc[0]));
+    }
+    double a = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+    }
+}
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* out) {
+    __shared__ double red[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += partial[i];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (threadIdx.x == 0) *out = a;
+    }
+}
+
 }  // namespace hq
 
 using namespace hq;
@@ -320,6 +368,25 @@ extern "C" int hq_state_norm2(const void* state, int L, double* out) {
     norm2_kernel<<<grid, block, 0, rt().compute>>>(static_cast<const double2*>(state), n, d);
     HQ_CUDA(cudaGetLastError());
     HQ_CUDA(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, rt().compute));
+    HQ_CUDA(cudaStreamSynchronize(rt().compute));
+    dev_free(d);
+    return HQ_OK;
+}
+
+// Probability that physical local bit `target_bit` reads 0 (reference: kernelMeasure, src/kernel.h:14).  HBM-bound: reads
+// 16 * 2^(L-1) bytes (the "bit clear" half; whole 32-byte sectors for target_bit 0, i.e. 16 * 2^L there).
+extern "C" int hq_state_measure(const void* state, int L, int target_bit, double* p0) {
+    HQ_REQUIRE(rt().ready && state && p0 && L >= 1 && target_bit >= 0 && target_bit < L, "bad arguments to hq_state_measure");
+    const uint64_t half = 1ull << (L - 1);
+    const int block = 256;
+    const int grid = (int)std::min<uint64_t>((half + block - 1) / block, (uint64_t)rt().sm_count * 8);
+    double* d = nullptr;
+    HQ_CUDA(dev_alloc(reinterpret_cast<void**>(&d), (size_t)(grid + 1) * 8));
+    measure_kernel<<<grid, block, 0, rt().compute>>>(static_cast<const double2*>(state), half, target_bit, d + 1);
+    HQ_CUDA(cudaGetLastError());
+    sum_partials_kernel<<<1, 256, 0, rt().compute>>>(d + 1, grid, d);
+    HQ_CUDA(cudaGetLastError());
+    HQ_CUDA(cudaMemcpyAsync(p0, d, 8, cudaMemcpyDeviceToHost, rt().compute));
     HQ_CUDA(cudaStreamSynchronize(rt().compute));
     dev_free(d);
     return HQ_OK;

@@ -143,6 +143,20 @@ extern "C" int hq_circuit_execute(hq_circuit* h, int* time_us, double* device_ms
     return HQ_OK;
 }
 
+// Frees the resident state vector (run(destroy = false) / prepare_state keep it); the compiled schedule and its plans stay.
+extern "C" int hq_circuit_release_state(hq_circuit* h) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    h->c->destroyState();
+    return HQ_OK;
+}
+
+extern "C" int hq_circuit_measure(hq_circuit* h, int qubit, double* p0) {
+    if (!h || !p0) { g_cerr = "null argument"; return HQ_ERR_ARG; }
+    if (qubit < 0 || qubit >= h->c->numQubits) { g_cerr = "qubit out of range"; return HQ_ERR_ARG; }
+    *p0 = h->c->measure(qubit);
+    return HQ_OK;
+}
+
 extern "C" int hq_circuit_norm2(hq_circuit* h, double* out) {
     if (!h || !out) { g_cerr = "null argument"; return HQ_ERR_ARG; }
     *out = h->c->norm2();

@@ -165,6 +165,23 @@ double Circuit::swapAloneMs() {
     return ms;
 }
 
+// P(logical qubit reads 0) over the whole distributed state.  A local qubit is a reduction over this shard's "bit clear" half; a
+// global qubit selects whole shards (those whose rank bit is 0 contribute their norm).  Collective: every rank calls it.
+double Circuit::measure(int logicalQubit) {
+    if (deviceStateVec.empty()) return 0.0;
+    const int L = numQubits - MyGlobalVars::bit;
+    const int p = schedule.finalState.pos.empty() ? logicalQubit : schedule.finalState.pos[logicalQubit];
+    double mine = 0;
+    if (p < L) checkHq(hq_state_measure(deviceStateVec[0], L, p, &mine))
+    else if (!((MyMPI::rank >> (p - L)) & 1)) checkHq(hq_state_norm2(deviceStateVec[0], L, &mine))
+    if (MyGlobalVars::numGPUs == 1) return mine;
+    std::vector<double> all(MyGlobalVars::numGPUs);
+    checkHq(hq_comm_allgather_host(&mine, all.data(), sizeof(double)));
+    double total = 0;
+    for (double v : all) total += v;
+    return total;
+}
+
 double Circuit::norm2() {
     double v = 0;
     if (!deviceStateVec.empty()) checkHq(hq_state_norm2(deviceStateVec[0], numQubits - MyGlobalVars::bit, &v));

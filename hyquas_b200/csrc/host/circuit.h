@@ -41,6 +41,7 @@ public:
     std::string stateDump();                                 // the text printState() prints
     bool fullState(std::vector<qComplex>& out);              // all 2^n amplitudes in LOGICAL order (single process, small n)
     bool localShard(double* out);                            // this process' amplitudes in PHYSICAL order
+    double measure(int logicalQubit);                        // P(qubit reads 0) over the distributed state (collective)
     double norm2();                                          // sum |a|^2 over this process' shard
     double swapAloneMs();                                    // the schedule's exchanges with no compute (collective)
     std::string compileError() const;                        // why compile() would refuse (empty: it would not)

@@ -360,9 +360,77 @@ void Compiler::rebalance(std::vector<GateGroup>& groups, int nEff) const {
     }
 }
 
+// A launch with a handful of gates still costs a full sweep.  Its gates may be able to run EARLIER: gate g of a small group j can
+// close group i < j when g's non-diagonal target lies in group i's tile and g commutes with everything that runs in between
+// (the groups i+1 .. j-1 and the gates of group j that stay ahead of it).  If every gate of the small group finds such a home
+// the group disappears and the schedule is one sweep shorter (qaoa_30: 7 -> 5 sweeps, supremacy_30: 10 -> 9).
+static bool gatesCommute(const Gate& a, const Gate& b) {
+    auto acts = [](const Gate& g, qindex& nd, qindex& d) {
+        nd = d = 0;
+        (g.isDiagonal() ? d : nd) |= qindex(1) << g.targetQubit;
+        if (g.controlQubit >= 0) d |= qindex(1) << g.controlQubit;
+        if (g.controlQubit2 >= 0) d |= qindex(1) << g.controlQubit2;
+    };
+    qindex an, ad, bn, bd;
+    acts(a, an, ad);
+    acts(b, bn, bd);
+    return !(an & (bn | bd)) && !(bn & ad);
+}
+
+void Compiler::absorbCrumbs(std::vector<GateGroup>& groups, int nEff) const {
+    if (!rebalanceGroups) return;
+    Evaluator* ev = Evaluator::getInstance();
+    const double sweep = ev->perfPerGate(nEff, std::vector<Gate>());
+    for (size_t j = groups.size(); j-- > 1;) {
+        if (groups[j].backend != Backend::PerGate || groups[j].gates.size() > 24) continue;
+        std::vector<std::vector<Gate>> added(j);          // gates appended to group i < j so far
+        bool all = true;
+        double extra = 0;
+        for (const Gate& g : groups[j].gates) {
+            int home = -1;
+            for (int i = (int)j - 1; i >= 0; i--) {        // nearest group first
+                // g would run at the end of group i: it must pass everything already placed after group i ...
+                bool pass = true;
+                for (size_t m = (size_t)i + 1; m < j && pass; m++) {
+                    for (const Gate& o : groups[m].gates) if (!gatesCommute(g, o)) { pass = false; break; }
+                    for (const Gate& o : added[m]) if (pass && !gatesCommute(g, o)) { pass = false; break; }
+                }
+                if (!pass) break;                          // ... and nothing further back can be reached either
+                const bool fits = groups[i].backend == Backend::PerGate && (g.isDiagonal() || (groups[i].relatedQubits >> g.targetQubit & 1)) &&
+                                  (int)(groups[i].gates.size() + added[i].size()) < maxGroupGates;
+                if (fits) { home = i; break; }
+                // not in this tile: g may still hop over group i as a whole if it commutes with all of it
+                for (const Gate& o : groups[i].gates) if (!gatesCommute(g, o)) { pass = false; break; }
+                for (const Gate& o : added[i]) if (pass && !gatesCommute(g, o)) { pass = false; break; }
+                if (!pass) break;
+            }
+            if (home < 0) { all = false; break; }
+            added[home].push_back(g);
+        }
+        if (!all) continue;
+        for (size_t i = 0; i < j; i++) {
+            if (added[i].empty()) continue;
+            std::vector<Gate> merged = groups[i].gates;
+            merged.insert(merged.end(), added[i].begin(), added[i].end());
+            extra += ev->perfPerGate(nEff, merged) - groups[i].predictedMs;
+        }
+        if (extra >= std::max(groups[j].predictedMs, sweep)) continue;   // dearer than the sweep it saves
+        for (size_t i = 0; i < j; i++) {
+            if (added[i].empty()) continue;
+            groups[i].gates.insert(groups[i].gates.end(), added[i].begin(), added[i].end());
+            groups[i].predictedMs = ev->perfPerGate(nEff, groups[i].gates);
+        }
+        groups.erase(groups.begin() + j);
+    }
+}
+
 std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal, qindex exclude) const {
     std::vector<GateGroup> out = cutGroupsBothWays(stageGates, state, nLocal, exclude);
-    rebalance(out, nLocal - bitCount(exclude));
+    const int nEff = nLocal - bitCount(exclude);
+    rebalance(out, nEff);
+    const size_t before = out.size();
+    absorbCrumbs(out, nEff);
+    if (out.size() != before) rebalance(out, nEff);
     return out;
 }
 

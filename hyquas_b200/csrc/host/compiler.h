@@ -35,6 +35,7 @@ private:
     std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     std::vector<GateGroup> cutGroupsBothWays(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     void rebalance(std::vector<GateGroup>& groups, int nEff) const;
+    void absorbCrumbs(std::vector<GateGroup>& groups, int nEff) const;
     std::vector<GateGroup> cutGroupsGreedy(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     int numQubits;
     int numLocal;

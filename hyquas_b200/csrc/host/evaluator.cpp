@@ -47,6 +47,7 @@ Evaluator::Evaluator() {
     instrMs30 = 0.060;      // h_x256_4q: 512 instructions per amplitude in 30.8 ms
     jitRoundMs30 = 0.9;     // supremacy_30 launches: 112-124 instructions per amplitude in 3-5 rounds take 9.6-11.6 ms
     jitBaseMs30 = 0.3;
+    jitUnderSweepMs30 = 0.015;
     const double dense[8] = {2.75, 2.75, 2.75, 2.75, 5.0, 9.7, 18.3, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
     for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
 }
@@ -117,6 +118,7 @@ void Evaluator::loadParam(int numQubits) {
         else if (key == "instr_ms30") in >> instrMs30;
         else if (key == "jit_round_ms30") in >> jitRoundMs30;
         else if (key == "jit_base_ms30") in >> jitBaseMs30;
+        else if (key == "jit_under_sweep_ms30") in >> jitUnderSweepMs30;
         else if (key == "specialised") { int v; in >> v; specialised = v != 0; }
         else if (key == "dense_base_ms30") in >> denseBaseMs30;
         else if (key == "gate") { int i; double v; in >> i >> v; if (i >= 0 && i < 32) gateNs[i] = v; }
@@ -224,7 +226,9 @@ double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
         // every round after the first moves the tile through shared memory once more (64 KB out, 64 KB in per tile: 0.9 ms per
         // 2^30 amplitudes at 128 B/clk/SM) and flushes the pending coefficients (<= 2 instructions per amplitude)
         const double compute = jitBaseMs30 + instrMs30 * (instr + 2.0 * rounds) + jitRoundMs30 * (rounds - 1);
-        return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
+        // sweep-bound launches still pay a little for their arithmetic (the overlap of HBM, FP64 and shared-memory phases is
+        // not perfect): r02_s6, supremacy_30: 14 instructions per amplitude 5.75 ms, 49 -> 6.5, 76 -> 6.6, 98 -> 7.6
+        return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30() + jitUnderSweepMs30 * instr, compute);
     }
     double compute = groupBaseMs30;
     qindex targets = 0;

@@ -46,6 +46,7 @@ public:
     double instrMs30;                       // ms per (FP64 instruction per amplitude) over 2^30 amplitudes
     double jitRoundMs30;                    // coefficient flush + shared-memory exchange of one extra round
     double jitBaseMs30;
+    double jitUnderSweepMs30;               // what an instruction per amplitude costs a launch that is sweep-bound
     static double instrPerAmp(const Gate& g);
     static int registerRounds(const std::vector<Gate>& gates);   // rounds the tile kernel will need for this group
 private:

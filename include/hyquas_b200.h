@@ -68,6 +68,8 @@ int hq_amp_fetch(const void* state, int64_t idx, double out_re_im[2]);
  * never travel to the host: returns physical local indices (ascending) with |a|^2 > thresh. */
 int hq_dump_scan(const void* state, int L, double thresh, int64_t* idx_out, double* amp_out, int64_t cap, int64_t* found);
 int hq_state_norm2(const void* state, int L, double* out);
+/* kernelMeasure (src/kernel.h:14, src/kernelSimple.cu:482-516): probability that physical local bit target_bit reads 0 */
+int hq_state_measure(const void* state, int L, int target_bit, double* p0);
 
 /* ---- gate-group kernel (replaces copyGatesToSymbol + launchExecutor, src/kernel.h:25-28,
  *      src/kernelOpt.cu:425-433,499-506, and the mask bookkeeping of Executor::prepareBitMap /

@@ -35,7 +35,9 @@ int hq_circuit_run(hq_circuit* c, int copy_back, int destroy, int* time_us, doub
  * per_group_ms (optional): CUDA-event time of each gate-group launch (MEASURE_STAGE, src/executor.cpp:406-458). */
 int hq_circuit_prepare_state(hq_circuit* c);
 int hq_circuit_execute(hq_circuit* c, int* time_us, double* device_ms, float* per_group_ms, int cap, int* ngroups);
+int hq_circuit_release_state(hq_circuit* c);                  /* free the resident state, keep the compiled schedule */
 int hq_circuit_norm2(hq_circuit* c, double* out);
+int hq_circuit_measure(hq_circuit* c, int qubit, double* p0);   /* P(logical qubit reads 0); collective (kernelMeasure, src/kernel.h:14) */
 /* the schedule's global<->local exchanges alone, back to back (collective; leaves the state permuted) */
 int hq_circuit_swap_alone_ms(hq_circuit* c, double* ms);
 int hq_circuit_io_bytes(const hq_circuit* c, size_t* h2d_plan_bytes, size_t* d2h_dump_bytes);

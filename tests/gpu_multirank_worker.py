@@ -36,6 +36,7 @@ def main():
         # ampAt is collective (broadcast from the owner): every rank asks for the same indices and gets the same values
         probes = [0, 5, (1 << n) - 1, (1 << (n - 1)) + 77]
         amps = [c.amp_at(i) for i in probes]
+        p0 = [c.measure(q) for q in (0, n // 2, n - 1)]           # collective too
         gathered = [torch.empty(shard.size * 2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(shard.view(np.float64).copy()), gathered, dst=0)
         if rank == 0:
@@ -50,6 +51,8 @@ def main():
             err = float(np.max(np.abs(got - want)))
             ok, derr = O.compare_dumps(O.dump_state(want, n), dump)
             ok = ok and all(abs(a - want[i]) <= 1e-10 for a, i in zip(amps, probes))
+            for q, p in zip((0, n // 2, n - 1), p0):
+                ok = ok and abs(p - float(np.sum(np.abs(want[((logical >> q) & 1) == 0]) ** 2))) <= 1e-10
             status = "ok" if err <= 1e-10 and ok else "MISMATCH"
             bad += status != "ok"
             print(f"[multi-gpu x{world}] {name}: stages={info['stages']} groups={info['groups']} max|d|={err:.2e} dump={ok} {status}",

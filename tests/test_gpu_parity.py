@@ -193,6 +193,31 @@ def test_full_size_norm_after_circuit(gpu_runtime):
     c.close()
 
 
+def test_measure_matches_numpy(gpu_runtime):
+    """hq_state_measure / Circuit.measure (kernelMeasure, src/kernelSimple.cu:482-516): P(bit = 0) for every qubit of a random
+    state and after a circuit whose final layout is the identity or not; 1e-12 absolute."""
+    from hyquas_b200._lib import check, lib
+    n = 18
+    st = _random_state(n, 21)
+    dev = ctypes.c_void_p()
+    check(lib.hq_state_alloc(n, ctypes.byref(dev)))
+    check(lib.hq_state_upload(dev, n, 0, 1 << n, st.ctypes.data))
+    idx = np.arange(1 << n)
+    for t in range(n):
+        p0 = ctypes.c_double()
+        check(lib.hq_state_measure(dev, n, t, ctypes.byref(p0)))
+        assert abs(p0.value - float(np.sum(np.abs(st[((idx >> t) & 1) == 0]) ** 2))) <= 1e-12
+    check(lib.hq_state_free(dev))
+    text = C.generate("qaoa_20")
+    c = _run(gpu_runtime, text)
+    _, gates = O.parse_qasm(text)
+    want = O.simulate(20, gates)
+    idx = np.arange(1 << 20)
+    for q in (0, 7, 19):
+        assert abs(c.measure(q) - float(np.sum(np.abs(want[((idx >> q) & 1) == 0]) ** 2))) <= 1e-12
+    c.close()
+
+
 def test_dump_scan_and_fetch(gpu_runtime):
     from hyquas_b200._lib import check, lib
     n = 16

@@ -119,6 +119,36 @@ def main():
             per = {"total_ms": round(ms_pg, 3), "launch_ms": [round(x, 3) for x in per_ms],
                    "launch_backend": [g["backend"][0] for g in groups for _ in range(g["launches"])],
                    "swap_and_gaps_ms": round(ms_pg - sum(per_ms), 3)}
+        hidden = None
+        if world > 1 and os.environ.get("HQ_SUITE_OVERLAP_PROBE"):
+            # the same circuit with the per-chunk overlap groups switched off, and the schedule's exchanges alone
+            import ctypes
+            from hyquas_b200._lib import check, lib
+            os.environ["HQ_ENABLE_OVERLAP"] = "0"
+            c2 = api.Circuit.from_qasm(text)
+            c2.compile()
+            os.environ.pop("HQ_ENABLE_OVERLAP", None)
+            c.release_state()       # one state at a time (128 GiB per GPU at L = 33); the p2p mapping follows the live state
+            c2.prepare_state()
+            c2.execute()
+            off = None
+            for _ in range(reps):
+                c2.prepare_state()
+                dist.barrier()
+                t = torch.tensor([c2.execute()[1]], dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                off = float(t.item()) if off is None else min(off, float(t.item()))
+            sw = ctypes.c_double()
+            check(lib.hq_circuit_swap_alone_ms(c2._h, sw))
+            check(lib.hq_circuit_swap_alone_ms(c2._h, sw))      # second pass: warm
+            t = torch.tensor([sw.value], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            swap_ms = float(t.item())
+            hidden = {"time_overlap_off_ms": round(off, 3), "swap_alone_ms": round(swap_ms, 3), "off_sweeps": c2.schedule_info()["groups"],
+                      "hidden_frac": round((off - best) / swap_ms, 3) if swap_ms > 0 else None}
+            c2.close()
+            c.prepare_state()
+            c.execute()             # the state whose norm / dump are checked below
         norm = torch.tensor([c.norm2()], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(norm)
@@ -142,7 +172,8 @@ def main():
                               "effective_tbps": round(bytes_ / (best * 1e-3) / 1e12, 3),
                               "sweeps_per_s": round(S / (best * 1e-3), 2),
                               "predicted_ms": round(sum(g["predicted_ms"] for g in groups), 2),
-                              "check": verdict, "ok": ok, **({"per_group": per} if per else {})}), flush=True)
+                              "check": verdict, "ok": ok, **({"overlap": hidden} if hidden else {}),
+                              **({"per_group": per} if per else {})}), flush=True)
         c.close()
     if world > 1:
         dist.barrier()
