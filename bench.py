@@ -361,7 +361,8 @@ def run_ours(args, world, rank, local_rank):
 
     # ---- parity on the product path, before anything is timed ----------------------------------------------
     fam = args.circuit
-    parity_names = [f"{fam}_{22 + g}", f"qaoa_{22 + g}"] if not args.no_parity else []
+    # small instances of the workload family and of qaoa (needs an even qubit count), 22-24 qubits in all, 10+ local qubits
+    parity_names = [f"{fam}_{22 + g}", f"qaoa_{22 + 2 * ((g + 1) // 2)}"] if not args.no_parity else []
     parity, parity_ok = (None, True)
     if parity_names:
         parity, parity_ok = parity_block(api, world, rank, dist, torch, parity_names)

@@ -477,9 +477,8 @@ extern "C" int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int 
     // Which shape?  Measured at 2^30 amplitudes (profiles/r01_s10_microbench.json = 3 CTAs/SM single buffer, r01_s11 = double
     // buffer): the double buffer wins where one matrix dominates the tile's time (m = 6: 18.8 vs 20.9 ms; a lone m <= 3:
     // 5.4 vs 5.9 ms) and loses where several small matrices share a launch (m4: 7.5 vs 6.0, m4x2: 12.1 vs 10.4, m3x3: 10.6 vs
-    // 8.8) -- eight warps cannot cover the barriers between matrices.  While a swap kernel is co-resident the double-buffered
-    // shape is the one that leaves it a slot on every SM.
-    const bool db_pays = maxm >= 6 || (plan->p.nmat == 1 && maxm <= 3) || rt().reserved_ctas > 0;
+    // 8.8) -- eight warps cannot cover the barriers between matrices.
+    const bool db_pays = maxm >= 6 || (plan->p.nmat == 1 && maxm <= 3);
     const bool db = (want_db < 0 ? db_pays : want_db != 0) && smem_db <= 227 * 1024;
     auto kern = db ? (maxm <= 4 ? dense_kernel<4, true> : dense_kernel<6, true>) : (maxm <= 4 ? dense_kernel<4, false> : dense_kernel<6, false>);
     const size_t smem = db ? smem_db : plan->smem;
@@ -487,9 +486,8 @@ extern "C" int hq_dense_plan_launch(const hq_dense_plan* plan, void* state, int 
     HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, DENSE_THREADS, smem));
     DenseParams p = plan->p;
     p.state = static_cast<double2*>(state);
-    // a co-resident swap kernel (16K registers per CTA, no shared memory) fits next to the one double-buffered CTA of an SM;
-    // the single-buffer shape fills the register file and must leave slots free instead
-    const int reserve = db ? 0 : rt().reserved_ctas;
+    // an exchange kernel in flight owns rt().reserved_ctas whole SMs (fat CTAs, see swap.cu): leave them out of the grid
+    const int reserve = rt().reserved_ctas * std::max(1, nb);
     plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * std::max(1, nb) - reserve));
     kern<<<plan->grid, DENSE_THREADS, smem, on_comm_stream ? rt().comm : rt().compute>>>(p);
     HQ_CUDA(cudaGetLastError());

@@ -95,6 +95,7 @@ struct Emitter {
     int thread_of_tile[16]; // tile bit -> thread-id bit or -1
     double deferred = 1.0;  // product of the common factors left out of earlier rounds' stores
     int stat_fp = 0;        // FP64 instructions emitted per thread (statistics)
+    int stat_fused = 0;     // blocks emitted as one product matrix
     bool ok = true;         // false: the plan holds something the emitter does not understand (caller falls back)
 
     Emitter(const hq_group_plan& p, bool h) : plan(p), host(h) {
@@ -326,18 +327,150 @@ struct Emitter {
         }
     }
 
+    // ---- block fusion -------------------------------------------------------------------------------------------------
+    // Consecutive static ops (no run-time predicate) of a round whose register bits -- target and register-bit controls -- stay
+    // within ONE or TWO register qubits form a block.  A block can be emitted gate by gate, or as the product matrix of its
+    // gates (2x2 or 4x4 complex, composed here on the host) applied once: u3 ; u3 on a qubit costs 3 instead of 6 instructions
+    // per scalar, the eight u3 and three cx of a quantum-volume SU(4) block 7 instead of 24, while two butterflies on two
+    // qubits stay cheaper gate by gate (2 against 3).  Both forms are emitted on a trial basis and the shorter one is kept.
+    // Blocks on disjoint register bits commute, so several stay open at once; anything that does not commute with a block (a
+    // predicated op or a run-time diagonal on one of its bits) closes it first.
+    struct Block { uint32_t bits; std::vector<const DevOp*> ops; };
+
+    void apply_dense(const std::vector<cplx>& M, const std::vector<int>& bits) {   // M: 2^m x 2^m row-major on register bits `bits`
+        const int m = (int)bits.size(), K = 1 << m;
+        uint32_t bmask = 0;
+        for (int b : bits) bmask |= 1u << b;
+        for (int base = 0; base < R; ++base) {
+            if (base & bmask) continue;
+            std::vector<int> idx(K);
+            for (int j = 0; j < K; ++j) {
+                int v = base;
+                for (int b = 0; b < m; ++b) if (j >> b & 1) v |= 1 << bits[b];
+                idx[j] = v;
+            }
+            std::vector<Term> nr(K), ni(K);
+            for (int i = 0; i < K; ++i) {
+                std::vector<Term> tr, ti;
+                for (int j = 0; j < K; ++j) {
+                    const cplx c = M[(size_t)i * K + j];
+                    tr.push_back(sc(re[idx[j]], c.real())); tr.push_back(sc(im[idx[j]], -c.imag()));
+                    ti.push_back(sc(im[idx[j]], c.real())); ti.push_back(sc(re[idx[j]], c.imag()));
+                }
+                nr[i] = lincomb(tr);
+                ni[i] = lincomb(ti);
+            }
+            for (int i = 0; i < K; ++i) { re[idx[i]] = nr[i]; im[idx[i]] = ni[i]; }
+        }
+    }
+
+    void emit_static_op(const DevOp& op) {
+        const uint32_t kind = op.code / 24, tb = (op.code % 24) / 6;
+        cplx M[4];
+        decode2x2(op, kind, M);
+        apply2x2(M, (int)tb, op.creg);
+    }
+
+    void emit_block(const Block& blk) {
+        if (blk.ops.size() == 1 || !fuse_blocks()) { for (const DevOp* op : blk.ops) emit_static_op(*op); return; }
+        std::vector<int> bits;
+        for (int b = 0; b < RBITS; ++b) if (blk.bits >> b & 1) bits.push_back(b);
+        const int m = (int)bits.size(), K = 1 << m;
+        // product of the block's gates on its own 2^m-dimensional space: apply each gate to the columns of the identity
+        std::vector<cplx> U((size_t)K * K, 0.0);
+        for (int i = 0; i < K; ++i) U[(size_t)i * K + i] = 1.0;
+        auto local = [&](int regbit) { for (int b = 0; b < m; ++b) if (bits[b] == regbit) return b; return -1; };
+        for (const DevOp* op : blk.ops) {
+            const uint32_t kind = op->code / 24, tb = (op->code % 24) / 6;
+            cplx G[4];
+            decode2x2(*op, kind, G);
+            const int t = local((int)tb);
+            int cmask = 0;
+            for (int b = 0; b < RBITS; ++b) if (op->creg >> b & 1) cmask |= 1 << local(b);
+            for (int col = 0; col < K; ++col)
+                for (int lo = 0; lo < K; ++lo) {
+                    if ((lo >> t & 1) || (lo & cmask) != cmask) continue;
+                    const int hi = lo | (1 << t);
+                    const cplx a = U[(size_t)lo * K + col], b = U[(size_t)hi * K + col];
+                    U[(size_t)lo * K + col] = G[0] * a + G[1] * b;
+                    U[(size_t)hi * K + col] = G[2] * a + G[3] * b;
+                }
+        }
+        for (cplx& v : U) {   // entries that are zero / real / imaginary up to rounding are made exactly so (they decide what is emitted)
+            if (std::abs(v) < 1e-15) v = 0.0;
+            else if (std::fabs(v.imag()) < 1e-15 * std::abs(v)) v = cplx(v.real(), 0.0);
+            else if (std::fabs(v.real()) < 1e-15 * std::abs(v)) v = cplx(0.0, v.imag());
+        }
+        // trial emission of both forms; keep the one with fewer FP64 instructions
+        const size_t o0 = o.size();
+        const int v0 = nvar, f0 = stat_fp;
+        Term r0[R], i0[R];
+        std::memcpy(r0, re, sizeof(re));
+        std::memcpy(i0, im, sizeof(im));
+        for (const DevOp* op : blk.ops) emit_static_op(*op);
+        const int eager = stat_fp - f0;
+        o.resize(o0); nvar = v0; stat_fp = f0;
+        std::memcpy(re, r0, sizeof(re));
+        std::memcpy(im, i0, sizeof(im));
+        apply_dense(U, bits);
+        const int fused = stat_fp - f0;
+        if (fused <= eager) { ++stat_fused; return; }
+        o.resize(o0); nvar = v0; stat_fp = f0;
+        std::memcpy(re, r0, sizeof(re));
+        std::memcpy(im, i0, sizeof(im));
+        for (const DevOp* op : blk.ops) emit_static_op(*op);
+    }
+
+    static bool fuse_blocks() { static const bool on = getenv("HQ_JIT_NO_FUSE") == nullptr; return on; }
+
     void emit_ops(const DevRound& rd) {
+        std::vector<Block> open;
+        auto close_touching = [&](uint32_t bits) {
+            for (size_t i = 0; i < open.size();) {
+                if (open[i].bits & bits) { emit_block(open[i]); open.erase(open.begin() + i); }
+                else ++i;
+            }
+        };
         for (int k = rd.op_begin; k < rd.op_end; ++k) {
             const DevOp& op = ops[k];
-            if (op.code == CODE_DIAG_RUN) { emit_diag_run(&op); k += (int)op.aux; continue; }
-            if (op.code == CODE_DIAG_T) { emit_diag_t(op); continue; }
-            const uint32_t kind = op.code / 24, tb = (op.code % 24) / 6;
-            cplx M[4];
-            decode2x2(op, kind, M);
-            const std::string cc = pred_all(op.cphys);
-            if (cc.empty()) apply2x2(M, (int)tb, op.creg);
-            else { cond_begin(cc); apply2x2(M, (int)tb, op.creg); cond_end(); }
+            if (op.code == CODE_DIAG_RUN) {
+                // a factor on every amplitude of the thread commutes with all static ops; one restricted to some register
+                // bits is diagonal there and must follow what is pending on them
+                if (op.creg) close_touching(op.creg);
+                emit_diag_run(&op);
+                k += (int)op.aux;
+                continue;
+            }
+            if (op.code == CODE_DIAG_T) { if (op.creg) close_touching(op.creg); emit_diag_t(op); continue; }
+            const uint32_t tb = (op.code % 24) / 6;
+            const uint32_t S = (1u << tb) | op.creg;
+            if (op.cphys) {   // predicated: a section of its own
+                close_touching(S);
+                const uint32_t kind = op.code / 24;
+                cplx M[4];
+                decode2x2(op, kind, M);
+                cond_begin(pred_all(op.cphys)); apply2x2(M, (int)tb, op.creg); cond_end();
+                continue;
+            }
+            uint32_t uni = S;
+            for (const Block& b : open) if (b.bits & S) uni |= b.bits;
+            if (__builtin_popcount(uni) > 2) {   // would outgrow a 4x4 block
+                close_touching(S);
+                if (__builtin_popcount(S) > 2) { emit_static_op(op); continue; }
+                uni = S;
+            }
+            // merge the op and the open blocks it touches into one block (program order inside a block is kept by construction:
+            // blocks being merged act on disjoint bits, so their relative order is free)
+            Block nb;
+            nb.bits = uni;
+            for (size_t i = 0; i < open.size();) {
+                if (open[i].bits & S) { nb.ops.insert(nb.ops.end(), open[i].ops.begin(), open[i].ops.end()); open.erase(open.begin() + i); }
+                else ++i;
+            }
+            nb.ops.push_back(&op);
+            open.push_back(std::move(nb));
         }
+        close_touching(~0u);
     }
 
     // ---- rounds --------------------------------------------------------------------------------------------------------
@@ -420,8 +553,9 @@ struct Emitter {
         o += host ? jit_host_prologue() : jit_device_prologue();
         for (int r = 0; r < plan.nrounds; ++r) emit_round(r);
         o += host ? jit_host_epilogue() : jit_device_epilogue();
-        char tail[128];
-        snprintf(tail, sizeof(tail), "// fp64 instructions per thread per tile: %d (%.2f per amplitude)\n", stat_fp, stat_fp / (double)R);
+        char tail[192];
+        snprintf(tail, sizeof(tail), "// fp64 instructions per thread per tile: %d (%.2f per amplitude); %d fused blocks\n", stat_fp,
+                 stat_fp / (double)R, stat_fused);
         o += tail;
         return o;
     }

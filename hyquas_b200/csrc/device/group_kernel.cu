@@ -833,8 +833,8 @@ static int launch_k(const hq_group_plan* plan, GroupParams p, cudaStream_t s) {
         HQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, plan->NT, plan->smem));
         it = occupancy.emplace(plan->smem, std::max(1, nb)).first;
     }
-    // a swap kernel in flight holds one CTA slot on `reserved_ctas` SMs: leave those slots free (no second wave)
-    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, rt().sm_count * it->second - rt().reserved_ctas));
+    // an exchange kernel in flight owns `reserved_ctas` whole SMs: leave them out of the grid (no second wave)
+    plan->grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)std::max(1, (rt().sm_count - rt().reserved_ctas) * it->second));
     kern<<<plan->grid, plan->NT, plan->smem, s>>>(p);
     HQ_CUDA(cudaGetLastError());
     return HQ_OK;
@@ -849,7 +849,7 @@ extern "C" int hq_group_plan_launch(const hq_group_plan* plan, void* state, int 
     resolve_jit(plan);
     if (plan->jit) {
         // a CTA = two workers: at least two tiles per CTA when there are enough of them
-        plan->grid = (int)std::min<uint64_t>((p.ntiles + 1) / 2, (uint64_t)std::max(1, rt().sm_count * plan->jit_occupancy - rt().reserved_ctas));
+        plan->grid = (int)std::min<uint64_t>((p.ntiles + 1) / 2, (uint64_t)std::max(1, (rt().sm_count - rt().reserved_ctas) * plan->jit_occupancy));
         return jit_launch(static_cast<JitKernel*>(plan->jit), plan->grid, 2 * plan->NT, jit_smem_bytes(plan->K), s, state);
     }
     const bool relaxed = rt().relaxed_regs;   // fewer resident CTAs, no register cap (HQ_RELAXED_REGS=1)

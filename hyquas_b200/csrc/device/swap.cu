@@ -55,6 +55,7 @@ struct Comm {
     uint64_t piece_amps = 0;
     cudaEvent_t slot_filled[2] = {nullptr, nullptr}, slot_free[2] = {nullptr, nullptr};
     bool p2p = false;                   // transport (decided at init)
+    bool warmed = false;                // peer connections established (first hq_swap_attach)
     std::vector<double2*> peer_state;   // p2p: every rank's state allocation mapped here (own entry = own pointer)
     void* attached = nullptr;
     double* sync_buf = nullptr;         // 2 doubles for the barrier collectives
@@ -146,10 +147,8 @@ struct XchgParams {
     uint8_t seg_shift[8], seg_src[8];
     uint64_t seg_mask[8];
 };
-// Two shapes of the same kernel.  <8, 512>: nothing runs under this exchange -- 32 fat CTAs, 8 remote loads in flight per
-// thread.  <4, 256, 4>: gate groups run under the exchange -- many small CTAs (<= 64 registers, 16K registers per CTA) that fit
-// NEXT to the compute CTAs on an SM (the compute grids are shrunk by `reserved_ctas` slots to make that room), so neither
-// kernel has to wait for the other to drain.
+// <8, 512>: 32 fat CTAs, 8 remote loads in flight per thread; with gate groups under the exchange those 32 SMs are left to it
+// (rt().reserved_ctas) and the compute grids use the other 116.
 template <int UNROLL, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) xchg_kernel(const __grid_constant__ XchgParams P) {
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -228,6 +227,9 @@ extern "C" int hq_comm_init(int world, int rank, const unsigned char id_bytes[12
     if (rc != HQ_OK) return rc;
     ncclUniqueId id;
     std::memcpy(&id, id_bytes, 128);
+    // NCCL's own log lines (NCCL_DEBUG=VERSION/INFO in the environment) go to stdout by default: that is where printState's
+    // amplitude dump goes, and scripts/check_wrapper.sh diffs it against the goldens.  Send them to stderr unless told otherwise.
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     HQ_NCCL(c.api.CommInitRank(&c.comm, world, id, rank));
     c.world = world;
     c.rank = rank;
@@ -296,6 +298,20 @@ extern "C" int hq_swap_attach(void* state) {
         c.peer_state[r] = static_cast<double2*>(p);
     }
     c.attached = state;
+    // NCCL sets up its peer connections at the first use of each peer: do that here, outside any timed region (the first
+    // exchange of a fresh process otherwise carries ~0.3 s of connection setup: hyquas_main qft_28 on 2 GPUs, 365 ms "Time Cost")
+    if (!c.warmed) {
+        HQ_NCCL(c.AllReduce(c.sync_buf, c.sync_buf + 1, 1, ncclDouble, ncclSum, c.comm, rt().comm));
+        HQ_NCCL(c.api.GroupStart());
+        for (int r = 0; r < c.world; ++r) {
+            if (r == c.rank) continue;
+            HQ_NCCL(c.api.Send(c.sync_buf + 2, 1, ncclDouble, r, c.comm, rt().comm));
+            HQ_NCCL(c.api.Recv(c.sync_buf + 3, 1, ncclDouble, r, c.comm, rt().comm));
+        }
+        HQ_NCCL(c.api.GroupEnd());
+        HQ_CUDA(cudaStreamSynchronize(rt().comm));
+        c.warmed = true;
+    }
     return HQ_OK;
 }
 
@@ -335,6 +351,7 @@ extern "C" int hq_comm_destroy(void) {
     cudaStreamDestroy(c.unstage);
     c.world = 1;
     c.rank = 0;
+    c.warmed = false;
     return HQ_OK;
 }
 
@@ -477,9 +494,13 @@ extern "C" int hq_swap_begin(hq_swap_plan* p, void* state_v) {
         HQ_CUDA(cudaEventRecord(p->landed[p->myc], comm));   // nobody else touches the chunk that stays
         // every rank's earlier compute must be finished before anybody reads or writes its memory
         HQ_NCCL(c.AllReduce(c.sync_buf, c.sync_buf + 1, 1, ncclDouble, ncclSum, c.comm, comm));
-        int ctas = p->coresident ? 96 : 32;
+        // 32 fat CTAs (512 threads, 8 remote loads in flight each) carry the link at 680 GB/s per direction.  When gate groups run
+        // under the exchange they leave that many SMs to it: a specialised gate-group CTA (512 threads x 128 registers, 197 KB of
+        // shared memory) owns its SM, nothing fits next to it (r02_m2: with 96 small exchange CTAs "reserved" the compute
+        // grid shrank to 52 of 148 SMs and the overlap cost more than it hid).
+        int ctas = 32;
         if (const char* e = getenv(p->coresident ? "HQ_SWAP_CTAS_OVERLAP" : "HQ_SWAP_CTAS")) ctas = std::max(1, atoi(e));
-        rt().reserved_ctas = p->coresident ? ctas : 0;   // gate-group launches under the exchange leave these CTA slots free
+        rt().reserved_ctas = p->coresident ? ctas : 0;   // gate-group launches under the exchange leave these SMs free
         for (int xr = 1; xr < (1 << p->k); ++xr) {
             const int ch = p->myc ^ xr, peer = p->peer[xr];
             XchgParams xp = p->xp;
@@ -489,8 +510,7 @@ extern "C" int hq_swap_begin(hq_swap_plan* p, void* state_v) {
             xp.peer_bits = p->chunk_bits(p->myc);
             xp.count = chunk_amps / 2;
             xp.z0 = c.rank < peer ? 0 : chunk_amps / 2;
-            if (p->coresident) xchg_kernel<4, 256, 4><<<ctas, 256, 0, comm>>>(xp);
-            else xchg_kernel<8, 512, 1><<<ctas, 512, 0, comm>>>(xp);
+            xchg_kernel<8, 512, 1><<<ctas, 512, 0, comm>>>(xp);
             HQ_CUDA(cudaGetLastError());
             // pairwise barrier: the chunk is complete once BOTH halves are done
             HQ_NCCL(c.api.GroupStart());

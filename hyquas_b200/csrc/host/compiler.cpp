@@ -141,7 +141,22 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
 }
 
 // ---- stage split --------------------------------------------------------------------------------------
+// The split is greedy, and a greedy split is fragile (one merged gate pair can turn two stages into three, i.e. one more exchange
+// of the whole state): it is run with a few different tie-breaking orders and the result with the fewest stages -- then the
+// fewest swapped qubits -- is kept.
 std::vector<Compiler::Stage> Compiler::splitStages() const {
+    std::vector<Stage> best;
+    int bestSwapped = 1 << 30;
+    for (int variant = 0; variant < (MyGlobalVars::bit == 0 ? 1 : 3); variant++) {
+        std::vector<Stage> st = splitStagesVariant(variant);
+        int swapped = 0;
+        for (size_t s = 1; s < st.size(); s++) swapped += bitCount(st[s].locals & ~st[s - 1].locals);
+        if (best.empty() || st.size() < best.size() || (st.size() == best.size() && swapped < bestSwapped)) { best = std::move(st); bestSwapped = swapped; }
+    }
+    return best;
+}
+
+std::vector<Compiler::Stage> Compiler::splitStagesVariant(int variant) const {
     std::vector<Stage> stages;
     if (MyGlobalVars::bit == 0) {
         stages.push_back({gates, (qindex(1) << numQubits) - 1});
@@ -156,7 +171,9 @@ std::vector<Compiler::Stage> Compiler::splitStages() const {
         while (bitCount(locals) < numLocal) {
             const size_t base = hyquas::runnableGates(gates, remaining, locals, 4096).size();
             int best = -1; size_t bestGain = base;
-            for (int q = 0; q < numQubits; q++) {
+            for (int qi = 0; qi < numQubits; qi++) {
+                // variants differ in the order qubits are tried (ties go to the first one found)
+                const int q = variant == 0 ? qi : (variant == 1 ? numQubits - 1 - qi : (qi + numQubits / 2) % numQubits);
                 if (locals >> q & 1) continue;
                 const size_t gain = hyquas::runnableGates(gates, remaining, locals | qindex(1) << q, 4096).size();
                 // ties prefer qubits that are already local (fewer bits to swap)
@@ -576,19 +593,33 @@ Schedule Compiler::run() {
         if (tailGates.empty()) continue;
         std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
         const State& prevState = schedule.localGroups[s - 1].state;
-        const double underExchange = 1.15;   // per-chunk launches share SMs and HBM with the exchange kernel
+        const double underExchange = 1.3;    // per-chunk launches leave 32 of 148 SMs (and some HBM bandwidth) to the exchange kernel
+        // Chunks land one after the other (the one that stays at once, then one per exchange step); the deferred work of a chunk
+        // starts when the chunk has landed and the previous chunk's work is done, so the last chunk's share is always exposed:
+        // with k = 1 half of the deferred work cannot be hidden, with k = 3 an eighth (r02_m2: supremacy_31 on 2 GPUs lost
+        // 4 ms to a deferral that a max(exchange, work) model had priced as a 5 ms win).
+        auto pipelined = [&](double workMs) {
+            const int chunks = 1 << k;
+            const double w = workMs / chunks;
+            double done = 0;
+            for (int c = 0; c < chunks; c++) {
+                const double landed = commMs * c / (chunks - 1);
+                done = std::max(done, landed) + w;
+            }
+            return done;
+        };
         double bestCost = total(cutGroups(prev, prevState, numLocal, 0)) + commMs;
         size_t bestFirst = cand.size();
         double deferredMs = 0;
         for (size_t first = cand.size(); first-- > 0;) {
             deferredMs += cand[first].predictedMs * (1 << k) * underExchange;   // predictedMs is per chunk
-            if (deferredMs > commMs * overlapSlack * 1.5) break;
+            if (deferredMs > commMs * overlapSlack * 2.0) break;
             std::vector<int> ids;
             for (size_t i = first; i < cand.size(); i++) for (auto& g : cand[i].gates) ids.push_back(g.gateID);
             std::sort(ids.begin(), ids.end());
             std::vector<Gate> rest;
             for (auto& g : prev) if (!std::binary_search(ids.begin(), ids.end(), g.gateID)) rest.push_back(g);
-            const double cost = total(cutGroups(rest, prevState, numLocal, 0)) + std::max(commMs, deferredMs);
+            const double cost = total(cutGroups(rest, prevState, numLocal, 0)) + pipelined(deferredMs);
             // (a huge HQ_OVERLAP_SLACK forces the maximal deferral whatever it costs: tests of the per-chunk path at sizes
             // whose exchange is too short to be worth hiding)
             if (cost < bestCost - 1e-9 || overlapSlack > 1e6) { bestCost = cost; bestFirst = first; }

@@ -31,6 +31,7 @@ public:
 private:
     struct Stage { std::vector<Gate> gates; qindex locals; };
     std::vector<Stage> splitStages() const;
+    std::vector<Stage> splitStagesVariant(int variant) const;
     GateGroup denseCandidate(const std::vector<Gate>& gates, const std::vector<int>& remaining, const State& state, int numLocal, qindex exclude) const;
     std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     std::vector<GateGroup> cutGroupsBothWays(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;

@@ -116,12 +116,18 @@ int hq_dense_plan_info(const hq_dense_plan* plan, int* tile_bits, int* smem_byte
 int hq_dense_plan_destroy(hq_dense_plan* plan);
 int hq_dense_apply(void* state, int L, int m, const int* qubit_pos, const double* u_colmajor);   /* create+launch+destroy */
 
-/* ---- multi-GPU: one process per GPU, NCCL over NVLink (replaces the NCCL bootstrap of MyGlobalVars::init,
- *      src/utils.cpp:46-58, and Executor::transpose + all2all + sliceBarrier, src/executor.cpp:59-179,650-659).
- *      The swap trades the top k local bits with k global bits IN PLACE: the local state is 2^k contiguous chunks;
- *      chunk c goes to the rank whose swapped global bits equal c and is replaced by that rank's chunk.  Chunks move
- *      in pieces through a two-slot staging ring on the comm stream; hq_swap_wait_chunk() orders the compute stream
- *      behind one chunk at a time so that per-chunk gate groups overlap the rest of the exchange. -------------------- */
+/* ---- multi-GPU: one process per GPU (replaces the NCCL bootstrap of MyGlobalVars::init, src/utils.cpp:46-58, and
+ *      Executor::transpose + all2all + sliceBarrier, src/executor.cpp:59-179,650-659).
+ *      A swap trades k local bits with k global bits IN PLACE: the local state is 2^k chunks (the values of the k swapped local
+ *      bits); chunk c goes to the rank whose swapped global bits equal c and is replaced by that rank's chunk.  Two transports,
+ *      chosen at hq_comm_init (HQ_SWAP=p2p|nccl; p2p whenever every GPU pair is peer-capable):
+ *        p2p   the state allocations are mapped into every process (CUDA IPC, hq_swap_attach); one kernel per exchange step swaps
+ *              the two chunks of a rank pair element by element over NVLink.  No staging, no second buffer, and the swapped
+ *              local bits may be ANY positions >= 3 (hq_swap_any_position = 1): no local bit permutation is needed first.
+ *        nccl  chunks move in pieces through a two-slot staging ring (ncclSend/ncclRecv on the comm stream + un-stage copies);
+ *              the swapped bits must be the TOP k local positions (hq_state_bitswap brings them there).
+ *      Either way one event per chunk: hq_swap_wait_chunk() orders the compute stream behind one chunk at a time, so per-chunk
+ *      gate groups (plans created with fixed bits = the swapped positions) run under the rest of the exchange. ---------------- */
 typedef struct hq_swap_plan hq_swap_plan;
 int hq_comm_unique_id(unsigned char out[128]);                       /* ncclGetUniqueId (rank 0), to be broadcast by the host */
 int hq_comm_init(int world, int rank, const unsigned char id[128]);  /* ncclCommInitRank */

@@ -124,3 +124,33 @@ def test_cuda_flavour_compiles_for_sm100a(tmp_path):
     sp = re.search(r"(\d+) bytes spill stores", info)   # 32 amplitudes' scalars + temporaries at the 128-register cap:
     assert sp is None or int(sp.group(1)) <= 512, info   # a few spilled temporaries are tolerated, a spilled working set is not
     assert os.path.getsize(out) > 1000
+
+
+def test_block_fusion_shortens_su4_blocks_and_keeps_amplitudes():
+    """Quantum-volume style blocks (u3 u3 / cx / u3 u3 / cx ...) on register qubits are emitted as 4x4 product matrices when that
+    is cheaper: fewer FP64 instructions than gate by gate (HQ_JIT_NO_FUSE=1 in a child process), same amplitudes."""
+    import subprocess
+    import sys
+    n = 13
+    text = C.quantum_volume(n, depth=3, seed=11)
+    _, gates = O.parse_qasm(text)
+    keep = [g for g in gates if max(g.target, g.control) < 12]
+    plan = make_plan(n, 0xFFF, keep)
+    src = jit_source(plan, True)
+    fused = int(re.search(r"fp64 instructions per thread per tile: (\d+)", src).group(1))
+    assert int(re.search(r"(\d+) fused blocks", src).group(1)) > 0
+    st = random_state(n, 5)
+    want = st.copy()
+    O.apply(want, n, keep)
+    run_host_flavour(src, st)
+    lib.hq_group_plan_destroy(plan)
+    assert np.max(np.abs(st - want)) < 1e-13
+    code = ("import sys, re; sys.path.insert(0, %r)\n"
+            "from tests.test_jit_cpu import *\n"
+            "_, gates = O.parse_qasm(C.quantum_volume(13, depth=3, seed=11))\n"
+            "keep = [g for g in gates if max(g.target, g.control) < 12]\n"
+            "src = jit_source(make_plan(13, 0xFFF, keep), False)\n"
+            "print(re.search(r'fp64 instructions per thread per tile: (\\d+)', src).group(1))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, HQ_JIT_NO_FUSE="1"), timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert fused < 0.8 * int(r.stdout.strip())

@@ -78,11 +78,12 @@ def expected_dump(name, n, text):
 
 
 def main():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:   # torchrun pins one OpenMP thread per rank; the product compiles its specialised kernels on these threads
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or world) // world))
     import torch
     import torch.distributed as dist
     from hyquas_b200 import api, circuits as C
-
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     if world > 1:
         dist.init_process_group("gloo")
