@@ -333,6 +333,7 @@ def run_ours(args, world, rank, local_rank):
     # one OpenMP team per rank: the product compiles its specialised kernels on these threads (and rank 0 runs the oracle)
     if world > 1:
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or world) // world))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line
     import torch
     from hyquas_b200 import api
     import ctypes

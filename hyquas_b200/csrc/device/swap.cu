@@ -82,6 +82,10 @@ static int nccl_fail(ncclResult_t r, const char* what, int line) {
 static int load_nccl() {
     NcclApi& a = cm().api;
     if (a.handle) return HQ_OK;
+    // NCCL's own log lines (NCCL_DEBUG=VERSION/INFO in the environment) go to stdout by default: that is where printState's
+    // amplitude dump goes, and scripts/check_wrapper.sh diffs it against the goldens.  Send them to stderr unless told otherwise
+    // (before the library initialises: ncclGetUniqueId already prints the version line).
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
         a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         if (a.handle) break;
@@ -227,9 +231,6 @@ extern "C" int hq_comm_init(int world, int rank, const unsigned char id_bytes[12
     if (rc != HQ_OK) return rc;
     ncclUniqueId id;
     std::memcpy(&id, id_bytes, 128);
-    // NCCL's own log lines (NCCL_DEBUG=VERSION/INFO in the environment) go to stdout by default: that is where printState's
-    // amplitude dump goes, and scripts/check_wrapper.sh diffs it against the goldens.  Send them to stderr unless told otherwise.
-    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     HQ_NCCL(c.api.CommInitRank(&c.comm, world, id, rank));
     c.world = world;
     c.rank = rank;

@@ -399,7 +399,7 @@ void Compiler::absorbCrumbs(std::vector<GateGroup>& groups, int nEff) const {
     Evaluator* ev = Evaluator::getInstance();
     const double sweep = ev->perfPerGate(nEff, std::vector<Gate>());
     for (size_t j = groups.size(); j-- > 1;) {
-        if (groups[j].backend != Backend::PerGate || groups[j].gates.size() > 24) continue;
+        if (groups[j].gates.size() > 24) continue;   // (a small dense launch is a crumb too; its gates can only move into tile groups)
         std::vector<std::vector<Gate>> added(j);          // gates appended to group i < j so far
         bool all = true;
         double extra = 0;
