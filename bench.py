@@ -342,7 +342,19 @@ def run_ours(args, world, rank, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL prints its version line on stdout when NCCL_DEBUG is set in the environment; stdout carries the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            torch.cuda.set_device(local_rank)
+            dist.barrier()
+            api.init()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.cuda.set_device(local_rank)
     api.init()
     name, n, text = workload(args, world)
@@ -384,11 +396,13 @@ def run_ours(args, world, rank, local_rank):
     c.prepare_state()
 
     # ---- value: K executions on the resident state, CUDA events on the launching stream -------------------
+    # nvidia-smi needs a few hundred ms to deliver its first sample: start it before the warm-up so that short timed regions
+    # (5 steps of 70-90 ms) are covered too; samples therefore span warm-up + timed region, the same kernels at the same load
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         c.execute()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     dev_ms = 0.0
     for _ in range(args.steps):
         _, ms = c.execute()

@@ -23,6 +23,7 @@
 // NCCL is bound with dlopen (libnccl.so.2) so that single-GPU use never needs it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstring>
@@ -211,12 +212,24 @@ struct hq_swap_plan {
     }
 };
 
+// NCCL prints its version line (NCCL_DEBUG=VERSION / INFO in the environment) with a plain printf on stdout, which is where
+// printState's amplitude dump goes and what scripts/check_wrapper.sh diffs against the goldens: while NCCL initialises, fd 1
+// points at stderr.
+namespace {
+struct StdoutToStderr {
+    int saved;
+    StdoutToStderr() { fflush(stdout); saved = dup(1); if (saved >= 0) dup2(2, 1); }
+    ~StdoutToStderr() { if (saved >= 0) { fflush(stdout); dup2(saved, 1); close(saved); } }
+};
+}  // namespace
+
 extern "C" int hq_comm_unique_id(unsigned char out[128]) {
     HQ_REQUIRE(out != nullptr, "null out pointer");
     int rc = load_nccl();
     if (rc != HQ_OK) return rc;
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    StdoutToStderr quiet;
     HQ_NCCL(cm().api.GetUniqueId(&id));
     std::memcpy(out, &id, 128);
     return HQ_OK;
@@ -231,7 +244,10 @@ extern "C" int hq_comm_init(int world, int rank, const unsigned char id_bytes[12
     if (rc != HQ_OK) return rc;
     ncclUniqueId id;
     std::memcpy(&id, id_bytes, 128);
-    HQ_NCCL(c.api.CommInitRank(&c.comm, world, id, rank));
+    {
+        StdoutToStderr quiet;
+        HQ_NCCL(c.api.CommInitRank(&c.comm, world, id, rank));
+    }
     c.world = world;
     c.rank = rank;
     HQ_CUDA(cudaMalloc(&c.sync_buf, 4 * sizeof(double)));

@@ -289,9 +289,16 @@ std::string Circuit::stateDump() {
 }
 
 void Circuit::printState() {
-    if (MyMPI::rank != 0) return;
-    fputs(stateDump().c_str(), stdout);
-    fflush(stdout);
+    if (MyMPI::rank == 0) {
+        fputs(stateDump().c_str(), stdout);
+        fflush(stdout);
+    }
+    // The ranks of a launcher-mode run share one stdout: nobody prints its Logger lines into the middle of rank 0's dump
+    // (collective: every rank calls printState, as in the reference's main.cpp:246-249).
+    if (MyGlobalVars::numGPUs > 1 && !MyGlobalVars::hostOnly) {
+        unsigned char token = 0;
+        checkHq(hq_comm_bcast_host(&token, 1, 0));
+    }
 }
 
 bool Circuit::localShard(double* out) {

@@ -110,3 +110,50 @@ def test_compile_refuses_too_few_local_qubits_with_an_error_code():
     assert r.returncode == 0, r.stderr[-800:]
     assert "refused:" in r.stdout and "refused plan:" in r.stdout and "at least 10 are needed" in r.stdout
     assert "'stages'" in r.stdout
+
+
+def _param_file(path, h_us):
+    """A {L}qubits.out in the reference's layout (evaluator-preprocess/process.cpp:167-178) with hq_preprocess's marker."""
+    single = [100000] * 14
+    single[3] = h_us                      # H
+    lines = ["1"] + [f"{v} " for v in single] + [""] + [f"{v} " for v in [90000] * 7]
+    lines += [f"{1 << m} {0.5 * (m + 1):f}" for m in range(10)] + ["", "0.000000", "#hq_preprocess test"]
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+def test_evaluator_reads_reference_layout_parameter_files(tmp_path):
+    """Evaluator::loadParam reads {L}qubits.out files in the reference's layout (what hq_preprocess writes): the predicted time of
+    an H-heavy group follows the H entry of the file; a file without the marker on the default path would be ignored."""
+    import subprocess
+    import sys
+    code = ("from hyquas_b200 import api\n"
+            "api.init_host_only(1, 0)\n"
+            "c = api.Circuit(20)\n"
+            "for i in range(200): c.add_gate('H', 5 + i % 4); c.add_gate('T', 5 + i % 4)\n"
+            "c.compile(); print('PRED', sum(g['predicted_ms'] for g in c.groups()))\n")
+    preds = []
+    for h_us in (20000, 2000000):
+        d = tmp_path / f"p{h_us}"
+        d.mkdir()
+        _param_file(str(d / "20qubits.out"), h_us)
+        env = dict(os.environ, HYQUAS_PARAM_DIR=str(d), HQ_PEEPHOLE="0", HQ_BACKEND="group")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+        assert r.returncode == 0, r.stderr[-500:]
+        preds.append(float(re.search(r"PRED ([0-9.eE+-]+)", r.stdout).group(1)))
+    assert preds[1] > 10 * preds[0] > 0
+
+
+@pytest.mark.gpu
+def test_hq_preprocess_writes_the_reference_layout(tmp_path):
+    """hq_preprocess (the reference's `process` tool for this library): one file per L with param_type, 14 + 7 integer times,
+    ten `K ms` lines, one transpose line -- exactly what src/evaluator.cpp:60-103 parses -- plus the marker line."""
+    import subprocess
+    exe = os.path.join(ROOT, "hyquas_b200", "hq_preprocess")
+    r = subprocess.run([exe, "20"], capture_output=True, text=True, timeout=900, env=dict(os.environ, HYQUAS_PARAM_DIR=str(tmp_path)))
+    assert r.returncode == 0, (r.stdout[-300:], r.stderr[-500:])
+    tok = open(tmp_path / "20qubits.out").read().split("#hq_preprocess")[0].split()
+    assert tok[0] == "1" and len(tok) == 1 + 14 + 7 + 20 + 1
+    times = [int(t) for t in tok[1:22]]
+    assert all(t > 0 for t in times)
+    assert [int(tok[22 + 2 * i]) for i in range(10)] == [1 << i for i in range(10)]
+    assert all(float(tok[23 + 2 * i]) > 0 for i in range(10))
