@@ -593,7 +593,8 @@ Schedule Compiler::run() {
         if (tailGates.empty()) continue;
         std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
         const State& prevState = schedule.localGroups[s - 1].state;
-        const double underExchange = 1.3;    // per-chunk launches leave 32 of 148 SMs (and some HBM bandwidth) to the exchange kernel
+        const double underExchange = 1.55;   // per-chunk launches leave 32 of 148 SMs and some HBM bandwidth to the exchange kernel
+                                             // (r02_m8: supremacy_33, 1/8-state launches of 6.3 ms groups take 1.25 ms, not 0.79)
         // Chunks land one after the other (the one that stays at once, then one per exchange step); the deferred work of a chunk
         // starts when the chunk has landed and the previous chunk's work is done, so the last chunk's share is always exposed:
         // with k = 1 half of the deferred work cannot be hidden, with k = 3 an eighth (r02_m2: supremacy_31 on 2 GPUs lost

@@ -152,6 +152,11 @@ static bool isButterflyMat(const Gate& g) {
 // FP64 instructions per amplitude the specialised kernel emits for this gate (device/group_jit.cpp: every scalar is
 // coefficient x variable, a sum of n terms costs n - 1 instructions, products by constants are free until the round's flush).
 double Evaluator::instrPerAmp(const Gate& g) {
+    if (g.instrCost >= 0) return g.instrCost;
+    return g.instrCost = instrPerAmpUncached(g);
+}
+
+double Evaluator::instrPerAmpUncached(const Gate& g) {
     int nz[2] = {0, 0};
     bool unit = true;   // every non-zero entry is +-1 or +-i
     for (int r = 0; r < 2; r++)

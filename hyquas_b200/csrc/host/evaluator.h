@@ -48,6 +48,7 @@ public:
     double jitBaseMs30;
     double jitUnderSweepMs30;               // what an instruction per amplitude costs a launch that is sweep-bound
     static double instrPerAmp(const Gate& g);
+    static double instrPerAmpUncached(const Gate& g);
     static int registerRounds(const std::vector<Gate>& gates);   // rounds the tile kernel will need for this group
 private:
     Evaluator();

@@ -17,6 +17,7 @@ struct Gate {
     qComplex mat[2][2];
     std::string name;
     int targetQubit, controlQubit, controlQubit2;   // controls: -1 when absent
+    mutable double instrCost = -1.0;                // Evaluator::instrPerAmp's memo (a function of mat and the controls only)
     Gate(): gateID(0), type(GateType::ID), targetQubit(-1), controlQubit(-1), controlQubit2(-1) {}
 
     bool isControlGate() const { return controlQubit != -1; }
