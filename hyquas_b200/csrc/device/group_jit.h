@@ -1,6 +1,7 @@
 // Per-group specialised gate-group kernels: source emitter (group_jit.cpp) and NVRTC runtime + cache (group_jit_rt.cpp).
 #pragma once
 #include <cstddef>
+#include <functional>
 #include <string>
 
 struct hq_group_plan;
@@ -23,9 +24,11 @@ const char* jit_host_epilogue();
 struct JitKernel;   // one loaded cubin
 // Compile (or fetch from the in-memory / on-disk cache) and load.  Returns nullptr and sets `why` when NVRTC or the driver
 // entry points are unavailable or the compile fails; the caller then keeps the interpreter kernel.
-JitKernel* jit_get(const std::string& source, size_t dynamic_smem, std::string* why);
-// Compile a batch of sources on all host cores (cold cache), without loading; a later jit_get() finds them cached.
-void jit_precompile(const std::string* sources, int n);
+// `identity` = the bytes that determine the kernel (the plan); `emit` is only called on a cache miss.
+JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::function<std::string()>& emit, std::string* why);
+// Compile a batch on all host cores (cold cache), without loading; a later jit_get() finds them cached.
+void jit_precompile(const std::string* identities, int n, const std::function<std::string(int)>& emit);
+bool jit_cached(const std::string& identity);
 int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state);
 int jit_max_blocks_per_sm(JitKernel* k, int block, size_t smem);
 void jit_stats(int* kernels, int* compiled, int* disk_hits, double* compile_seconds);

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -128,13 +129,17 @@ uint64_t fnv(const std::string& s, uint64_t h) {
     for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
     return h;
 }
+const char* kEmitterVersion = "hqjit3";   // bump when group_jit.cpp changes what it emits for the same plan
 const char* kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "--ptxas-options=-v", "-lineinfo"};
-Key key_of(const std::string& src) {
-    std::string salt = "hqjit1|" + std::to_string(nvrtc().major) + "." + std::to_string(nvrtc().minor);
+// `what` identifies the kernel: the bytes of the plan it is generated from (see plan_identity() in group_kernel.cu), so that a
+// cache hit costs a hash of ~20 KB and no source emission at all.  Compiler version, options and the emitter's version salt
+// are part of the key.
+Key key_of(const std::string& what) {
+    std::string salt = std::string(kEmitterVersion) + "|" + std::to_string(nvrtc().major) + "." + std::to_string(nvrtc().minor);
     for (const char* o : kOptions) salt += std::string("|") + o;
     Key k;
-    k.a = fnv(src, fnv(salt, 0xcbf29ce484222325ull));
-    k.b = fnv(src, fnv(salt, 0x9e3779b97f4a7c15ull) ^ src.size());
+    k.a = fnv(what, fnv(salt, 0xcbf29ce484222325ull));
+    k.b = fnv(what, fnv(salt, 0x9e3779b97f4a7c15ull) ^ what.size());
     return k;
 }
 
@@ -258,15 +263,24 @@ bool jit_enabled() {
     return on;
 }
 
-void jit_precompile(const std::string* sources, int n) {
+bool jit_cached(const std::string& identity) {
+    if (!nvrtc().ok()) return false;
+    Cache& c = cache();
+    const Key k = key_of(identity);
+    std::lock_guard<std::mutex> lock(c.mu);
+    return c.loaded.count(k) || c.cubins.count(k);
+}
+
+// identities[i] names kernel i; emit(i) produces its source when (and only when) neither the memory nor the disk cache has it.
+void jit_precompile(const std::string* identities, int n, const std::function<std::string(int)>& emit) {
     if (!nvrtc().ok()) return;
     cache_dir();
     Cache& c = cache();
     std::vector<int> todo;
     std::vector<Key> keys(n);
     for (int i = 0; i < n; ++i) {
-        if (sources[i].empty()) continue;
-        keys[i] = key_of(sources[i]);
+        if (identities[i].empty()) continue;
+        keys[i] = key_of(identities[i]);
         std::lock_guard<std::mutex> lock(c.mu);
         bool dup = c.loaded.count(keys[i]) || c.cubins.count(keys[i]);
         for (int j : todo) if (!(keys[j] < keys[i]) && !(keys[i] < keys[j])) dup = true;
@@ -277,26 +291,47 @@ void jit_precompile(const std::string* sources, int n) {
     for (int j = 0; j < m; ++j) {
         const int i = todo[j];
         std::vector<char> cubin;
-        if (!obtain_cubin(keys[i], sources[i], cubin, nullptr)) continue;
+        if (!read_disk(keys[i], cubin)) {
+            const std::string src = emit(i);
+            if (src.empty() || !obtain_cubin(keys[i], src, cubin, nullptr)) continue;
+        } else {
+            std::lock_guard<std::mutex> lock(c.mu);
+            ++c.disk_hits;
+        }
         std::lock_guard<std::mutex> lock(c.mu);
         c.cubins[keys[i]] = std::move(cubin);
     }
 }
 
-JitKernel* jit_get(const std::string& source, size_t dynamic_smem, std::string* why) {
+JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::function<std::string()>& emit, std::string* why) {
     Driver& d = driver();
     if (!d.good) { if (why) *why = "CUDA driver entry points unavailable"; return nullptr; }
     if (!nvrtc().ok()) { if (why) *why = "libnvrtc not found"; return nullptr; }
     cache_dir();
     Cache& c = cache();
-    const Key k = key_of(source);
+    const Key k = key_of(identity);
     {
         std::lock_guard<std::mutex> lock(c.mu);
         auto it = c.loaded.find(k);
         if (it != c.loaded.end()) return it->second;
     }
     std::vector<char> cubin;
-    if (!obtain_cubin(k, source, cubin, why)) return nullptr;
+    bool have = false;
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        auto it = c.cubins.find(k);
+        if (it != c.cubins.end()) { cubin = it->second; have = true; }
+    }
+    if (!have && read_disk(k, cubin)) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        ++c.disk_hits;
+        have = true;
+    }
+    if (!have) {
+        const std::string src = emit();
+        if (src.empty()) { if (why) *why = "the emitter rejected this plan"; return nullptr; }
+        if (!obtain_cubin(k, src, cubin, why)) return nullptr;
+    }
     auto fail = [&](CUresult r, const char* what) {
         const char* s = nullptr;
         d.getErrorString(r, &s);

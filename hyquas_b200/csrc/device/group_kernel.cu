@@ -333,6 +333,8 @@ static void encode_2x2(uint32_t kind, const double* M, double* out) {
 
 using namespace hq;
 
+static std::string plan_identity(const hq_group_plan& plan);
+
 extern "C" int hq_group_tile_bits(void) { return rt().tile_bits; }
 extern "C" int hq_group_min_run_bits(void) { return MIN_RUN_BITS; }
 
@@ -773,10 +775,10 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
         p.tb = reinterpret_cast<const uint16_t*>(d + o_tb);
     }
     // the specialised kernel's source (compiled at the first launch, or for a whole schedule at once by hq_group_plans_warm)
-    if (rt().ready && jit_enabled()) plan->jit_source = jit_emit_source(*plan, false);
+    if (rt().ready && jit_enabled()) plan->jit_identity = plan_identity(*plan);
     if (const char* dir = getenv("HQ_JIT_DUMP_DIR")) {   // developer aid: keep every emitted source (works without a GPU)
         static int serial = 0;
-        const std::string src = plan->jit_source.empty() ? jit_emit_source(*plan, false) : plan->jit_source;
+        const std::string src = jit_emit_source(*plan, false);
         char name[512];
         snprintf(name, sizeof(name), "%s/group_%03d.cu", dir, serial++);
         if (FILE* f = fopen(name, "w")) { fputs(src.c_str(), f); fclose(f); }
@@ -785,12 +787,33 @@ extern "C" int hq_group_plan_create_ex(int L, uint64_t tile_mask, uint64_t fixed
     return HQ_OK;
 }
 
+// Everything the emitter reads from a plan, as bytes: two plans with the same identity get the same kernel, so the cache is
+// keyed on this and a hit never emits any source.
+static std::string plan_identity(const hq_group_plan& plan) {
+    std::string id;
+    auto put = [&](const void* p, size_t n) { id.append(static_cast<const char*>(p), n); };
+    const int hdr[6] = {plan.L, plan.K, plan.NT, plan.nrounds, plan.nops, jit_l2_prefetch_slots()};
+    put(hdr, sizeof(hdr));
+    put(&plan.tile_mask, 8);
+    put(&plan.fixed_mask, 8);
+    put(&plan.fixed_value, 8);
+    const char fuse = getenv("HQ_JIT_NO_FUSE") ? 0 : 1;
+    put(&fuse, 1);
+    for (const auto& m : plan.meta) {
+        put(m.reg, sizeof(m.reg));
+        for (int b : m.tbits) put(&b, sizeof(int));
+    }
+    put(plan.blob.data() + plan.o_rounds, (size_t)plan.nrounds * sizeof(DevRound));
+    put(plan.blob.data() + plan.o_ops, (size_t)plan.nops * sizeof(DevOp));
+    return id;
+}
+
 // Resolve the specialised kernel of a plan: memory cache, disk cache, or an NVRTC compile.
 static void resolve_jit(const hq_group_plan* plan) {
-    if (plan->jit || plan->jit_failed || plan->jit_source.empty()) return;
+    if (plan->jit || plan->jit_failed || plan->jit_identity.empty()) return;
     std::string why;
     const size_t smem = jit_smem_bytes(plan->K);
-    JitKernel* k = jit_get(plan->jit_source, smem, &why);
+    JitKernel* k = jit_get(plan->jit_identity, smem, [&] { return jit_emit_source(*plan, false); }, &why);
     if (!k) {
         plan->jit_failed = true;
         static bool warned = false;
@@ -804,10 +827,14 @@ static void resolve_jit(const hq_group_plan* plan) {
 extern "C" int hq_group_plans_warm(hq_group_plan* const* plans, int n) {
     HQ_REQUIRE(n >= 0 && (n == 0 || plans != nullptr), "bad plan list");
     if (!rt().ready || !jit_enabled()) return HQ_OK;
-    std::vector<std::string> src;
+    std::vector<std::string> ids;
+    std::vector<const hq_group_plan*> which;
     for (int i = 0; i < n; ++i)
-        if (plans[i] && !plans[i]->jit && !plans[i]->jit_failed && !plans[i]->jit_source.empty()) src.push_back(plans[i]->jit_source);
-    jit_precompile(src.data(), (int)src.size());
+        if (plans[i] && !plans[i]->jit && !plans[i]->jit_failed && !plans[i]->jit_identity.empty() && !jit_cached(plans[i]->jit_identity)) {
+            ids.push_back(plans[i]->jit_identity);
+            which.push_back(plans[i]);
+        }
+    if (!ids.empty()) jit_precompile(ids.data(), (int)ids.size(), [&](int i) { return jit_emit_source(*which[i], false); });
     for (int i = 0; i < n; ++i) if (plans[i]) resolve_jit(plans[i]);
     return HQ_OK;
 }

@@ -103,7 +103,7 @@ struct hq_group_plan {
     struct RoundMeta { int reg[hq::RBITS]; std::vector<int> tbits; };
     std::vector<RoundMeta> meta;
     uint64_t fixed_mask = 0, fixed_value = 0;
-    std::string jit_source;               // CUDA source of this plan's specialised kernel (empty: interpreter kernel only)
+    std::string jit_identity;             // what determines this plan's specialised kernel (cache key); empty: interpreter only
     mutable void* jit = nullptr;          // hq::JitKernel*, resolved at the first launch (or by hq_group_plans_warm)
     mutable bool jit_failed = false;
     mutable int jit_occupancy = 0;

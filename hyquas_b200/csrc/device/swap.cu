@@ -376,13 +376,13 @@ extern "C" int hq_comm_destroy(void) {
 extern "C" int hq_comm_bcast_host(void* buf, size_t bytes, int root) {
     Comm& c = cm();
     HQ_REQUIRE(c.comm && buf, "communicator not initialised");
-    void* d = nullptr;
-    HQ_CUDA(cudaMalloc(&d, bytes));
+    void* d = nullptr;   // pooled scratch: cudaMalloc / cudaFree next to a 16-128 GiB allocation cost milliseconds and synchronise the device
+    HQ_CUDA(dev_alloc(&d, bytes));
     HQ_CUDA(cudaMemcpyAsync(d, buf, bytes, cudaMemcpyHostToDevice, rt().comm));
     HQ_NCCL(c.api.Broadcast(d, d, bytes, ncclUint8, root, c.comm, rt().comm));
     HQ_CUDA(cudaMemcpyAsync(buf, d, bytes, cudaMemcpyDeviceToHost, rt().comm));
     HQ_CUDA(cudaStreamSynchronize(rt().comm));
-    cudaFree(d);
+    dev_free(d);
     return HQ_OK;
 }
 
@@ -390,14 +390,14 @@ extern "C" int hq_comm_allgather_host(const void* send, void* recv, size_t bytes
     Comm& c = cm();
     HQ_REQUIRE(c.comm && send && recv, "communicator not initialised");
     void *ds = nullptr, *dr = nullptr;
-    HQ_CUDA(cudaMalloc(&ds, bytes_per_rank));
-    HQ_CUDA(cudaMalloc(&dr, bytes_per_rank * c.world));
+    HQ_CUDA(dev_alloc(&ds, bytes_per_rank));
+    HQ_CUDA(dev_alloc(&dr, bytes_per_rank * c.world));
     HQ_CUDA(cudaMemcpyAsync(ds, send, bytes_per_rank, cudaMemcpyHostToDevice, rt().comm));
     HQ_NCCL(c.api.AllGather(ds, dr, bytes_per_rank, ncclUint8, c.comm, rt().comm));
     HQ_CUDA(cudaMemcpyAsync(recv, dr, bytes_per_rank * c.world, cudaMemcpyDeviceToHost, rt().comm));
     HQ_CUDA(cudaStreamSynchronize(rt().comm));
-    cudaFree(ds);
-    cudaFree(dr);
+    dev_free(ds);
+    dev_free(dr);
     return HQ_OK;
 }
 

@@ -48,6 +48,7 @@ Evaluator::Evaluator() {
     jitRoundMs30 = 0.9;     // supremacy_30 launches: 112-124 instructions per amplitude in 3-5 rounds take 9.6-11.6 ms
     jitBaseMs30 = 0.3;
     jitUnderSweepMs30 = 0.015;
+    fusionAware = getenv("HQ_EVAL_FUSION") != nullptr && atoi(getenv("HQ_EVAL_FUSION")) != 0;
     const double dense[8] = {2.75, 2.75, 2.75, 2.75, 5.0, 9.7, 18.3, 41.0};   // by matrix qubits (<= 3 padded to 3; 7 not built)
     for (int m = 0; m < 8; m++) denseMs30[m] = dense[m];
 }
@@ -191,6 +192,41 @@ double Evaluator::instrPerAmpUncached(const Gate& g) {
     return cost;
 }
 
+// What block fusion in the specialised kernels (device/group_jit.cpp: consecutive static ops within one or two register qubits
+// are emitted as their 2x2 / 4x4 product when that is shorter) can bring the instruction count down to, on logical qubits and
+// ignoring rounds, i.e. optimistically: a one-qubit block costs at most 6 instructions per amplitude, a two-qubit block 14.
+double Evaluator::fusedInstr(const std::vector<Gate>& gates) {
+    struct Block { qindex bits; double eager; };
+    std::vector<Block> open;
+    double total = 0;
+    auto close = [&](size_t i) {
+        const int nb = bitCount(open[i].bits);
+        total += std::min(open[i].eager, nb <= 1 ? 6.0 : 14.0);
+        open.erase(open.begin() + i);
+    };
+    for (const Gate& g : gates) {
+        qindex S = qindex(1) << g.targetQubit;
+        if (g.controlQubit >= 0) S |= qindex(1) << g.controlQubit;
+        if (g.controlQubit2 >= 0) S |= qindex(1) << g.controlQubit2;
+        const double c = instrPerAmp(g);
+        qindex uni = S;
+        for (const Block& b : open) if (b.bits & S) uni |= b.bits;
+        if (bitCount(uni) > 2) {
+            for (size_t i = 0; i < open.size();) { if (open[i].bits & S) close(i); else ++i; }
+            if (bitCount(S) > 2) { total += c; continue; }
+            uni = S;
+        }
+        Block nb{uni, c};
+        for (size_t i = 0; i < open.size();) {
+            if (open[i].bits & S) { nb.eager += open[i].eager; open.erase(open.begin() + i); }
+            else ++i;
+        }
+        open.push_back(nb);
+    }
+    while (!open.empty()) close(0);
+    return total;
+}
+
 // Register rounds the tile kernel's planner will need (device/group_kernel.cu: a round holds 4 register qubits; a gate joins the
 // current round when nothing it fails to commute with was left behind and its non-diagonal target is, or can still become, a
 // register qubit): the same greedy fill, on logical qubits.
@@ -227,6 +263,7 @@ double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
     if (specialised) {
         double instr = 0;
         for (const Gate& g : gates) instr += instrPerAmp(g);
+        if (fusionAware) instr = 0.25 * instr + 0.75 * fusedInstr(gates);
         const int rounds = registerRounds(gates);
         // every round after the first moves the tile through shared memory once more (64 KB out, 64 KB in per tile: 0.9 ms per
         // 2^30 amplitudes at 128 B/clk/SM) and flushes the pending coefficients (<= 2 instructions per amplitude)

@@ -49,6 +49,8 @@ public:
     double jitUnderSweepMs30;               // what an instruction per amplitude costs a launch that is sweep-bound
     static double instrPerAmp(const Gate& g);
     static double instrPerAmpUncached(const Gate& g);
+    static double fusedInstr(const std::vector<Gate>& gates);    // instruction count if every one- / two-qubit block fuses
+    bool fusionAware;                       // price tile groups with block fusion in mind (HQ_EVAL_FUSION=1; A/B knob)
     static int registerRounds(const std::vector<Gate>& gates);   // rounds the tile kernel will need for this group
 private:
     Evaluator();
