@@ -50,7 +50,7 @@ public:
     static double instrPerAmp(const Gate& g);
     static double instrPerAmpUncached(const Gate& g);
     static double fusedInstr(const std::vector<Gate>& gates);    // instruction count if every one- / two-qubit block fuses
-    bool fusionAware;                       // price tile groups with block fusion in mind (HQ_EVAL_FUSION=1; A/B knob)
+    bool fusionAware;                       // price tile groups with block fusion in mind (HQ_EVAL_FUSION=0 switches it off)
     static int registerRounds(const std::vector<Gate>& gates);   // rounds the tile kernel will need for this group
 private:
     Evaluator();
