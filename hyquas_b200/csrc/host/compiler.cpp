@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cassert>
+#include <map>
 #include <string>
 #include <unordered_map>
 
@@ -568,6 +569,7 @@ Schedule Compiler::run() {
     // pass 2: work to hide the exchange behind.  The stage split is greedy, so the head of stage s always needs the
     // incoming qubits; what CAN run while chunks are still on the wire is the tail of stage s-1 (the reference's moveToNext
     // + overlapGroups, src/compiler.cpp:34-68, src/executor.cpp:41-47), run chunk by chunk as the chunks land.
+    std::map<size_t, std::vector<GateGroup>> readyCuts;   // stage -> its full groups, when pass 2 already cut exactly that gate list
     for (size_t s = 1; s < stages.size() && enableOverlap; s++) {
         LocalGroup& lg = schedule.localGroups[s];
         const int k = (int)lg.swap.localBit.size();
@@ -609,10 +611,13 @@ Schedule Compiler::run() {
             }
             return done;
         };
-        double bestCost = total(cutGroups(prev, prevState, numLocal, 0)) + commMs;
+        // every candidate costs one cut of stage s-1 (milliseconds of compile time): the cut that wins is kept for pass 3, and at
+        // most four deferral depths are tried
+        std::vector<GateGroup> bestCut = cutGroups(prev, prevState, numLocal, 0);
+        double bestCost = total(bestCut) + commMs;
         size_t bestFirst = cand.size();
         double deferredMs = 0;
-        for (size_t first = cand.size(); first-- > 0;) {
+        for (size_t first = cand.size(); first-- > 0 && cand.size() - first <= 4;) {
             deferredMs += cand[first].predictedMs * (1 << k) * underExchange;   // predictedMs is per chunk
             if (deferredMs > commMs * overlapSlack * 2.0) break;
             std::vector<int> ids;
@@ -620,11 +625,13 @@ Schedule Compiler::run() {
             std::sort(ids.begin(), ids.end());
             std::vector<Gate> rest;
             for (auto& g : prev) if (!std::binary_search(ids.begin(), ids.end(), g.gateID)) rest.push_back(g);
-            const double cost = total(cutGroups(rest, prevState, numLocal, 0)) + pipelined(deferredMs);
+            std::vector<GateGroup> cut = cutGroups(rest, prevState, numLocal, 0);
+            const double cost = total(cut) + pipelined(deferredMs);
             // (a huge HQ_OVERLAP_SLACK forces the maximal deferral whatever it costs: tests of the per-chunk path at sizes
             // whose exchange is too short to be worth hiding)
-            if (cost < bestCost - 1e-9 || overlapSlack > 1e6) { bestCost = cost; bestFirst = first; }
+            if (cost < bestCost - 1e-9 || overlapSlack > 1e6) { bestCost = cost; bestFirst = first; bestCut.swap(cut); }
         }
+        readyCuts[s - 1] = std::move(bestCut);   // stage s-1 is final now: pass 3 need not cut it again
         if (bestFirst == cand.size()) continue;
         std::vector<int> ids;
         for (size_t i = bestFirst; i < cand.size(); i++) {
@@ -637,8 +644,11 @@ Schedule Compiler::run() {
         prev.swap(rest);
     }
     // pass 3: cut what is left of every stage into full groups
-    for (size_t s = 0; s < stages.size(); s++)
-        schedule.localGroups[s].fullGroups = cutGroups(stages[s].gates, schedule.localGroups[s].state, numLocal, 0);
+    for (size_t s = 0; s < stages.size(); s++) {
+        auto it = readyCuts.find(s);
+        if (it != readyCuts.end()) schedule.localGroups[s].fullGroups = std::move(it->second);
+        else schedule.localGroups[s].fullGroups = cutGroups(stages[s].gates, schedule.localGroups[s].state, numLocal, 0);
+    }
     schedule.finalState = state;
     return schedule;
 }
