@@ -29,6 +29,7 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
 // Compile a batch on all host cores (cold cache), without loading; a later jit_get() finds them cached.
 void jit_precompile(const std::string* identities, int n, const std::function<std::string(int)>& emit);
 bool jit_cached(const std::string& identity);
+void jit_release(JitKernel* k);   // the plan that fetched it is gone (unreferenced kernels may be evicted, 512 stay loaded)
 int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state);
 int jit_max_blocks_per_sm(JitKernel* k, int block, size_t smem);
 void jit_stats(int* kernels, int* compiled, int* disk_hits, double* compile_seconds);

@@ -18,6 +18,7 @@
 #include <sys/types.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -40,6 +41,8 @@ struct JitKernel {
     size_t smem_set = 0;
     int regs = 0;
     int spill_bytes = 0;
+    int refs = 0;             // plans holding this kernel (jit_get / jit_release)
+    uint64_t last_use = 0;    // for eviction: loaded modules are capped, the least recently fetched unreferenced one goes first
 };
 
 namespace {
@@ -148,6 +151,8 @@ struct Cache {
     std::map<Key, JitKernel*> loaded;
     std::map<Key, std::vector<char>> cubins;   // compiled or read from disk, not yet loaded (jit_precompile)
     int compiled = 0, disk_hits = 0;
+    uint64_t clock = 0;
+    size_t max_loaded = 512;   // loaded modules kept (HQ_JIT_MAX_LOADED)
     double compile_seconds = 0;
     std::string dir;
     bool dir_ready = false;
@@ -158,6 +163,7 @@ const std::string& cache_dir() {
     Cache& c = cache();
     if (c.dir_ready) return c.dir;
     c.dir_ready = true;
+    if (const char* e = getenv("HQ_JIT_MAX_LOADED")) c.max_loaded = (size_t)std::max(8, atoi(e));
     std::string base;
     if (const char* e = getenv("HQ_JIT_CACHE")) base = e;
     else if (const char* x = getenv("XDG_CACHE_HOME")) base = std::string(x) + "/hyquas_b200/jit";
@@ -313,7 +319,7 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
     {
         std::lock_guard<std::mutex> lock(c.mu);
         auto it = c.loaded.find(k);
-        if (it != c.loaded.end()) return it->second;
+        if (it != c.loaded.end()) { ++it->second->refs; it->second->last_use = ++c.clock; return it->second; }
     }
     std::vector<char> cubin;
     bool have = false;
@@ -351,8 +357,27 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
     d.funcGetAttribute(&jk->spill_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, jk->fn);
     std::lock_guard<std::mutex> lock(c.mu);
     c.cubins.erase(k);
+    jk->refs = 1;
+    jk->last_use = ++c.clock;
     c.loaded[k] = jk;
+    // a long-lived process that keeps compiling new circuits must not accumulate modules without bound
+    while (c.loaded.size() > c.max_loaded) {
+        auto victim = c.loaded.end();
+        for (auto it = c.loaded.begin(); it != c.loaded.end(); ++it)
+            if (it->second->refs == 0 && (victim == c.loaded.end() || it->second->last_use < victim->second->last_use)) victim = it;
+        if (victim == c.loaded.end()) break;   // everything is in use
+        d.moduleUnload(victim->second->mod);
+        delete victim->second;
+        c.loaded.erase(victim);
+    }
     return jk;
+}
+
+void jit_release(JitKernel* k) {
+    if (!k) return;
+    Cache& c = cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (k->refs > 0) --k->refs;
 }
 
 int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state) {

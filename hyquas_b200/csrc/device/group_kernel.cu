@@ -914,6 +914,7 @@ extern "C" int hq_group_plan_table_bytes(const hq_group_plan* plan, int* bytes) 
 extern "C" int hq_group_plan_destroy(hq_group_plan* plan) {
     if (!plan) return HQ_OK;
     if (plan->dev_blob) dev_free(plan->dev_blob);
+    if (plan->jit) jit_release(static_cast<JitKernel*>(plan->jit));
     delete plan;
     return HQ_OK;
 }
