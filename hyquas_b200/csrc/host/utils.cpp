@@ -92,6 +92,20 @@ static void selfSpawnIfNeeded() {
     int n = 1;
     while (n * 2 <= visible) n *= 2;
     if (want > 1) { int w = 1; while (w * 2 <= want) w *= 2; n = std::min(n, w); }
+    // A circuit file on the command line tells how many qubits there are: keep at least 20 of them local (a 2^20-amplitude shard
+    // is 16 MiB; below that more GPUs only add exchanges, and below 10 local qubits compile() refuses).
+    for (size_t a = 1; a < args.size() && want <= 1; a++) {
+        std::ifstream f(args[a]);
+        if (!f) continue;
+        std::string head(4096, '\0');
+        f.read(&head[0], (std::streamsize)head.size());
+        const size_t q = head.find("qreg");
+        const size_t lb = q == std::string::npos ? q : head.find('[', q);
+        if (lb == std::string::npos) continue;
+        const int qubits = atoi(head.c_str() + lb + 1);
+        while (n > 1 && qubits - get_bit(n) < 20) n /= 2;
+        break;
+    }
     if (n <= 1) return;
     const std::string port = "MASTER_PORT=" + std::to_string(20000 + (int)(getpid() % 20000));
     const std::string run = "TORCHELASTIC_RUN_ID=hq" + std::to_string((long long)time(nullptr));

@@ -156,7 +156,9 @@ def test_reference_main_on_our_library(gpu_runtime, golden_dir, name):
     import re
     import subprocess
     exe = _dropin("main")
-    r = subprocess.run([exe, os.path.join(golden_dir, name + ".qasm")], capture_output=True, text=True, timeout=300)
+    # one GPU here (on a multi-GPU box the library's launcher mode would drive all of them: tests/test_gpu_multi.py covers that)
+    r = subprocess.run([exe, os.path.join(golden_dir, name + ".qasm")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, HQ_NUM_GPUS="1"))
     assert r.returncode == 0, r.stderr[-500:]
     dump = "".join(l + "\n" for l in r.stdout.splitlines() if re.match(r"^\d+ \d\.\d+: ", l))
     assert dump == open(os.path.join(golden_dir, name + ".log")).read()
@@ -168,7 +170,7 @@ def test_reference_microbenchmark_on_our_library(gpu_runtime):
     the reference's own tools use it."""
     import subprocess
     exe = _dropin("two-group-h")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, HQ_NUM_GPUS="1"))
     assert r.returncode == 0, (r.stdout[-300:], r.stderr[-500:])
 
 
