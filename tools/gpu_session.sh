@@ -1,13 +1,16 @@
 #!/bin/bash
-# r02 session 9 (1 GPU): pinned low bits of every tile (HBM run length 512 / 256 / 128 B) vs number of sweeps
+# r02 session 10 (1 GPU): final state -- full GPU test-suite, smoke(), default bench both arms
 set -u
-O=gpurun_out/s9; mkdir -p $O
-for pb in 5 4 3; do
-echo "== HQ_PINNED_BITS=$pb"; HQ_PINNED_BITS=$pb HQ_SUITE_PER_GROUP=1 timeout 600 python tools/run_suite.py supremacy_30 qaoa_30 qft_30 basis_change_28 hidden_shift_30 2>/dev/null | tee $O/suite_pb$pb.jsonl | python -c "
-import sys, json
-for l in sys.stdin:
-    d=json.loads(l); print(d['circuit'], d['sweeps'], d['time_ms'], d['ok'], [round(x,2) for x in d['per_group']['launch_ms']][:12])
-"
-done
-G=sweep_lo7,sweep_hi7,sweep_spread7,sup5_x42_hi7,sup5_x42_spread7
-for pb in 5 3; do echo "== microbench geometry, pinned $pb (tile = pinned bits + 7 chosen + fill)"; HQ_PINNED_BITS=$pb timeout 300 python tools/microbench.py --qubits 30 --only $G 2>&1 | grep -E "sweep_|sup5" | cut -c1-90; done
+O=gpurun_out/s10; mkdir -p $O
+echo "== pytest -m gpu (all)"; timeout 1800 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
+if grep -q "failed" $O/pytest_gpu.log; then grep -E "^E |FAILED" $O/pytest_gpu.log | head -20; fi
+echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== bench reference (driver-style flags)"; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/bench_reference.json 2> $O/bench_reference.err; cut -c1-300 $O/bench_reference.json
+echo "== bench ours (driver-style flags)"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_ours.json 2> $O/bench_ours.err; tail -2 $O/bench_ours.err
+python - <<P
+import json
+d=json.loads([l for l in open("$O/bench_ours.json") if l.startswith("{")][0])
+print("ms", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["ms_per_step"], d["e2e"]["breakdown_ms"], "roofline", d["roofline"]["frac"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["sample"][:80], "clocks", d["clocks"], "launches", d["gpu_launches"], "parity", d["parity"]["ok"])
+print([(g["gates"], g["ms"], g["predicted_ms"]) for g in d["groups"]])
+P
+echo "== hyquas_main, single GPU, golden"; ./hyquas_b200/hyquas_main tests/golden/bv_28.qasm 2>/dev/null | grep -v Logger | diff -q - tests/golden/bv_28.log && echo "bv_28 golden identical"

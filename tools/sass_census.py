@@ -50,27 +50,27 @@ def main():
     print("# SASS opcode census (round 2)\n")
     print(f"`cuobjdump -sass {os.path.relpath(lib, ROOT)}` (sm_100a), per kernel:\n")
     print(table(census(lib)))
-    # one specialised kernel: a supremacy-like group of ~100 gates on a 12-bit tile
-    import numpy as np  # noqa: F401
-    from hyquas_b200 import circuits as C
-    from hyquas_b200._lib import HqGate, check, lib as L
-    from oracle import oracle as O
-    _, gates = O.parse_qasm(C.supremacy(20, cycles=10, seed=5))
-    keep = [g for g in gates if (g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target < 12]
-    arr = (HqGate * len(keep))()
-    for i, g in enumerate(keep):
-        arr[i].type, arr[i].target, arr[i].control, arr[i].control2 = 0, g.target, g.control, g.control2
-        m = g.mat.reshape(4)
-        for j in range(4):
-            arr[i].mat[2 * j], arr[i].mat[2 * j + 1] = m[j].real, m[j].imag
-    plan = ctypes.c_void_p()
-    check(L.hq_group_plan_create(20, 0xFFF, arr, len(keep), ctypes.byref(plan)))
-    need = ctypes.c_size_t()
-    check(L.hq_debug_group_plan_jit_source(plan, 0, None, 0, ctypes.byref(need)))
-    buf = ctypes.create_string_buffer(need.value)
-    check(L.hq_debug_group_plan_jit_source(plan, 0, buf, need.value, ctypes.byref(need)))
-    rounds, fp = ctypes.c_int(), ctypes.c_double()
-    check(L.hq_group_plan_cost(plan, rounds, fp))
+    # one specialised kernel: the largest gate group of supremacy_24 as the product's own partitioner cuts it (host-only
+    # compile, no GPU; HQ_JIT_DUMP_DIR keeps every emitted kernel source)
+    from hyquas_b200 import api, circuits as C
+    from hyquas_b200._lib import check, lib as L
+    with tempfile.TemporaryDirectory() as dump:
+        os.environ["HQ_JIT_DUMP_DIR"] = dump
+        os.environ["HQ_BACKEND"] = "group"
+        api.init_host_only(1, 0)
+        c = api.Circuit.from_qasm(C.generate("supremacy_24"))
+        c.compile()
+        groups = c.groups()
+        big = max(range(len(groups)), key=lambda i: groups[i]["gates"])
+        rounds, fp = ctypes.c_int(), ctypes.c_double()
+        check(L.hq_circuit_group_cost(c._h, big, rounds, fp))
+        src = open(os.path.join(dump, "group_%03d.cu" % big)).read()
+        ngates = groups[big]["gates"]
+        c.close()
+    class _Buf:
+        value = src.encode()
+    buf = _Buf()
+    keep = [None] * ngates
     with tempfile.TemporaryDirectory() as d:
         cubin = os.path.join(d, "k.cubin")
         log = ctypes.create_string_buffer(1 << 16)
