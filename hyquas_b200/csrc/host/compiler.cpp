@@ -148,8 +148,11 @@ Compiler::Compiler(int numQubits_, std::vector<Gate> inputGates)
 std::vector<Compiler::Stage> Compiler::splitStages() const {
     std::vector<Stage> best;
     int bestSwapped = 1 << 30;
-    for (int variant = 0; variant < (MyGlobalVars::bit == 0 ? 1 : 3); variant++) {
-        std::vector<Stage> st = splitStagesVariant(variant);
+    const int nvar = MyGlobalVars::bit == 0 ? 1 : 3;
+    std::vector<std::vector<Stage>> tried(nvar);
+    for (int variant = 0; variant < nvar; variant++) tried[variant] = splitStagesVariant(variant);
+    for (int variant = 0; variant < nvar; variant++) {
+        std::vector<Stage>& st = tried[variant];
         int swapped = 0;
         for (size_t s = 1; s < st.size(); s++) swapped += bitCount(st[s].locals & ~st[s - 1].locals);
         if (best.empty() || st.size() < best.size() || (st.size() == best.size() && swapped < bestSwapped)) { best = std::move(st); bestSwapped = swapped; }
@@ -595,8 +598,10 @@ Schedule Compiler::run() {
         if (tailGates.empty()) continue;
         std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
         const State& prevState = schedule.localGroups[s - 1].state;
-        const double underExchange = 1.55;   // per-chunk launches leave 32 of 148 SMs and some HBM bandwidth to the exchange kernel
-                                             // (r02_m8: supremacy_33, 1/8-state launches of 6.3 ms groups take 1.25 ms, not 0.79)
+        // Per-chunk launches leave 32 of 148 SMs and some HBM bandwidth to the exchange kernel.  Measured (r02_m8, supremacy_33:
+        // 1/8-state launches of 6.3 ms groups take 1.25 ms, not 0.79) the slowdown is ~1.5; the chooser was measured with 1.3
+        // (8 GPUs: hidden_frac 0.42-0.65) and with 1.55 (4 GPUs: 0.24-0.47): the more eager setting hides more, it stays.
+        const double underExchange = 1.3;
         // Chunks land one after the other (the one that stays at once, then one per exchange step); the deferred work of a chunk
         // starts when the chunk has landed and the previous chunk's work is done, so the last chunk's share is always exposed:
         // with k = 1 half of the deferred work cannot be hidden, with k = 3 an eighth (r02_m2: supremacy_31 on 2 GPUs lost
