@@ -511,7 +511,11 @@ std::vector<GateGroup> Compiler::cutGroupsGreedy(const std::vector<Gate>& stageG
         gg.state = state;
         for (int gi : take) gg.gates.push_back(stageGates[gi]);
         gg.predictedMs = Evaluator::getInstance()->perfPerGate(nEff, gg.gates);
-        if (backendMode != 1 && nEff >= 8) {
+        // A tile launch that is (nearly) sweep-bound cannot lose to a dense launch: that one costs at least a sweep too and, needing
+        // every operand of its gates inside its blocks, never holds more gates.  Growing the dense candidate is the expensive part
+        // of the hybrid cut (6 of 10 ms for supremacy_30), so it is only done for compute-bound tile groups.
+        const bool tileIsSweepBound = gg.predictedMs <= 1.35 * Evaluator::getInstance()->perfPerGate(nEff, std::vector<Gate>());
+        if (backendMode != 1 && nEff >= 8 && (backendMode == 3 || nEff < 10 || !tileIsSweepBound)) {
             // hybrid choice (the reference's AdvanceCompiler::run, src/compiler.cpp:250-278): price a dense launch for
             // the same frontier and keep whichever costs fewer predicted milliseconds per gate
             GateGroup dense = denseCandidate(stageGates, remaining, state, nLocal, exclude);
