@@ -170,3 +170,28 @@ def test_hybrid_prefers_dense_for_quantum_volume(monkeypatch):
     c.compile()
     assert all(g["backend"] == "tile" for g in c.groups())
     c.close()
+
+
+@pytest.mark.parametrize("knob", ["HQ_REBALANCE", "HQ_PEEPHOLE_MERGE", "HQ_EVAL_FUSION"])
+@pytest.mark.parametrize("name", ["supremacy_16", "qaoa_16", "quantum_volume_14"])
+def test_round2_passes_are_optional_and_equivalent(monkeypatch, knob, name):
+    """Group rebalancing / crumb absorption, the single-qubit merge pass and the fusion-aware evaluator only change HOW the gates
+    are scheduled: with each of them switched off the compiled schedule still reproduces the oracle's amplitudes."""
+    monkeypatch.setenv(knob, "0")
+    text = C.generate(name)
+    n, got, info = emulate_circuit(text)
+    _, gates = O.parse_qasm(text)
+    assert np.max(np.abs(got - O.simulate(n, gates))) < 1e-12
+
+
+def test_supremacy_30_schedule_stays_short_and_balanced():
+    """The headline workload: at most 10 sweeps, no dense launch (the specialised tile kernel rides the sweep where a dense launch
+    costs 9 ms), and after rebalancing no group predicted above twice the sweep time."""
+    api.init_host_only(1, 0)
+    c = api.Circuit.from_qasm(C.generate("supremacy_30"))
+    c.compile()
+    groups = c.groups()
+    assert len(groups) <= 10 and all(g["backend"] == "tile" for g in groups)
+    sweep = min(g["predicted_ms"] for g in groups)
+    assert max(g["predicted_ms"] for g in groups) < 2.0 * sweep
+    c.close()

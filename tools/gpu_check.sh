@@ -1,7 +1,8 @@
 #!/bin/bash
-# r02 session 10 (1 GPU): final state -- full GPU test-suite, smoke(), default bench both arms
+# One-GPU acceptance run (one `gpurun` call): full GPU test-suite, smoke(), bench both arms with driver-style flags, CLI vs golden.
+#   gpurun --timeout 1500 -- bash tools/gpu_check.sh        (outputs under gpurun_out/check/)
 set -u
-O=gpurun_out/s10; mkdir -p $O
+O=gpurun_out/check; mkdir -p $O
 echo "== pytest -m gpu (all)"; timeout 1800 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
 if grep -q "failed" $O/pytest_gpu.log; then grep -E "^E |FAILED" $O/pytest_gpu.log | head -20; fi
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -1,5 +1,6 @@
 #!/bin/bash
-# r02 multi-GPU session (N = number of GPUs of the box): product-path parity, launcher mode, bench both arms, suite with overlap probe
+# Multi-GPU acceptance run (one `gpurun --gpus N` call): product-path parity, launcher mode, bench both arms, suite with overlap probe.
+#   gpurun --gpus 8 --timeout 1500 -- "LOG2N=3 bash tools/gpu_check_multi.sh 8"     (outputs under gpurun_out/m8/)
 set -u
 N=${1:-2}
 O=gpurun_out/m$N; mkdir -p $O
