@@ -61,6 +61,8 @@ _SIGS = {
     "hq_group_plan_local_exchanges": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_group_plan_destroy": (_c.c_int, [_c.c_void_p]),
     "hq_group_plan_cost": (_c.c_int, [_c.c_void_p, _P(_c.c_int), _P(_c.c_double)]),
+    "hq_group_plan_enable_zero_input": (_c.c_int, [_c.c_void_p]),
+    "hq_group_plan_launch_from_zero": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int]),
     "hq_group_plans_warm": (_c.c_int, [_P(_c.c_void_p), _c.c_int]),
     "hq_group_plan_is_specialised": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_jit_available": (_c.c_int, [_P(_c.c_int)]),

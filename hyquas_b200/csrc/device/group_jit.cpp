@@ -83,6 +83,7 @@ struct Term { int var; double c; };
 struct Emitter {
     const hq_group_plan& plan;
     const bool host;
+    bool zero_in = false;   // the launch's input is |0...0> (amplitude 0 = 1 on the rank that holds it): nothing is read from HBM
     std::string o;          // the source being written
     int nvar = 0;
     Term re[R], im[R];
@@ -499,6 +500,9 @@ struct Emitter {
         line(std::string("const u32 tin = ") + (lin_in ? "tj" : "HQ_SWZ(tj)") + ";");
         for (int i = 0; i < R; ++i) {
             const int a = fresh(), b = fresh();
+            if (zero_in && r == 0)   // the only non-zero input amplitude is index 0 of tile 0 (linear position 0 of the first tile)
+                line("double " + V(a) + " = (z0 && (tin ^ " + hex32(rd.ro_in[i]) + ") == 0u) ? 1.0 : 0.0, " + V(b) + " = 0.0;");
+            else
             line("double " + V(a) + ", " + V(b) + "; HQ_LD(tin ^ " + hex32(rd.ro_in[i]) + ", " + V(a) + ", " + V(b) + ");");
             re[i] = Term{a, last ? deferred : 1.0};
             im[i] = Term{b, last ? deferred : 1.0};
@@ -550,6 +554,7 @@ struct Emitter {
         o = head;
         o += "#define HQ_TILE_BASE(t) (" + tile_base_expr() + ")\n";
         o += "#define HQ_RUN_OFF(q) (" + deposit("q", run_dep, true) + ")\n";
+        if (zero_in) o += "#define HQ_ZERO_INPUT 1\n";
         o += host ? jit_host_prologue() : jit_device_prologue();
         for (int r = 0; r < plan.nrounds; ++r) emit_round(r);
         o += host ? jit_host_epilogue() : jit_device_epilogue();
@@ -619,10 +624,25 @@ __device__ __forceinline__ void prefetch_tile_l2(const double2* state, u64 t, u3
 #define HQ_SYNCWARP() __syncwarp()
 #define HQ_ROUND_DONE()
 // every thread of the worker holds its amplitudes in registers: the buffer can take the tile three slots ahead
+#ifdef HQ_ZERO_INPUT
+// Input = |0...0>: there is nothing to load (and nobody zero-filled the state): each worker keeps one private tile buffer for the
+// exchanges between rounds, the first round starts from constants, every tile is written as usual.
+#define HQ_TILE_CONSUMED()
+extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2* __restrict__ state, int amp0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 tid = threadIdx.x & (NT - 1);
+    const u32 wk = threadIdx.x / NT;
+    const u32 nslots = blockIdx.x < NTILES ? (u32)((NTILES - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    double2* tile = reinterpret_cast<double2*>(smem_raw + (size_t)wk * TILE * 16);
+    for (u32 s = wk; s < nslots; s += 2) {
+      const u64 tbase = HQ_TILE_BASE((u64)blockIdx.x + (u64)s * gridDim.x);
+      const bool z0 = amp0 != 0 && tbase == 0;
+      if (s >= 2) HQ_SYNC();   // the previous tile's last round has read this buffer
+#else
 #define HQ_TILE_CONSUMED() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); HQ_SYNC(); \
         if (s + 3 < nslots) issue_tile_load(state, (u64)blockIdx.x + (u64)(s + 3) * gridDim.x, tile, bar + (s + 3) % 6u, tid, NT); \
         if (PF_SLOTS > 3 && s + PF_SLOTS < nslots && tid < 32) prefetch_tile_l2(state, (u64)blockIdx.x + (u64)(s + PF_SLOTS) * gridDim.x, tid); }
-extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2* __restrict__ state) {
+extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2* __restrict__ state, int amp0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* bar = reinterpret_cast<u64*>(smem_raw + (size_t)3 * TILE * 16);
     const u32 tid = threadIdx.x & (NT - 1);
@@ -640,6 +660,7 @@ extern "C" __global__ void __launch_bounds__(2 * NT, MINB) hq_group_jit(double2*
       double2* tile = reinterpret_cast<double2*>(smem_raw + (size_t)b * TILE * 16);
       mbar_wait(bar + s % 6u, (s / 6u) & 1u);
       const u64 tbase = HQ_TILE_BASE((u64)blockIdx.x + (u64)s * gridDim.x);
+#endif
 )SRC";
 }
 const char* jit_device_epilogue() { return "    }\n}\n"; }
@@ -666,19 +687,23 @@ static inline double hq_xs(double v, int s) { u64 b; std::memcpy(&b, &v, 8); b ^
 #define HQ_ROUND_DONE()
 // one function per round would be tidier, but the arithmetic text must be the device text: a round is a block scope that the
 // host skeleton runs once per thread id through this macro pair
-extern "C" void hq_group_jit_host(double* state_re_im) {
+extern "C" void hq_group_jit_host(double* state_re_im, int amp0) {
     double2* state = reinterpret_cast<double2*>(state_re_im);
     std::vector<double2> bufA(TILE), bufB(TILE);
     for (u64 t = 0; t < NTILES; ++t) {
       const u64 tbase = HQ_TILE_BASE(t);
+      const bool z0 = amp0 != 0 && tbase == 0; (void)z0;
       double2* cur = bufA.data(); double2* nxt = bufB.data();
+#ifndef HQ_ZERO_INPUT
       for (u32 q = 0; q < NRUNS; ++q) std::memcpy(cur + (size_t)q * RUN_AMPS, state + tbase + HQ_RUN_OFF(q), (size_t)RUN_AMPS * 16);
+#endif
 )SRC";
 }
 const char* jit_host_epilogue() { return "    }\n}\n"; }
 
-std::string jit_emit_source(const hq_group_plan& plan, bool host) {
+std::string jit_emit_source(const hq_group_plan& plan, bool host, bool zero_input) {
     Emitter e(plan, host);
+    e.zero_in = zero_input;
     std::string src = e.run();
     if (!e.ok) return std::string();
     return src;
@@ -700,9 +725,10 @@ extern "C" int hq_group_plan_cost(const hq_group_plan* plan, int* rounds, double
     return HQ_OK;
 }
 
+// host_flavour: 0 = CUDA source, 1 = host source; +2 = the zero-input variant (input |0...0>, nothing loaded)
 extern "C" int hq_debug_group_plan_jit_source(const hq_group_plan* plan, int host_flavour, char* out, size_t cap, size_t* needed) {
     HQ_REQUIRE(plan != nullptr && needed != nullptr, "null argument");
-    const std::string src = hq::jit_emit_source(*plan, host_flavour != 0);
+    const std::string src = hq::jit_emit_source(*plan, (host_flavour & 1) != 0, (host_flavour & 2) != 0);
     HQ_REQUIRE(!src.empty(), "the JIT emitter rejected this plan");
     *needed = src.size() + 1;
     if (out && cap >= src.size() + 1) std::memcpy(out, src.c_str(), src.size() + 1);

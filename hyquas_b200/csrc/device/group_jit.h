@@ -11,7 +11,7 @@ namespace hq {
 // CUDA C++ source of the kernel `hq_group_jit(double2* state)` that applies exactly this plan (host = false), or of the
 // serial C++ function `hq_group_jit_host(double* state)` with the same arithmetic text (host = true; CPU tests only).
 // Empty string: the emitter does not handle this plan (the interpreter kernel does).
-std::string jit_emit_source(const hq_group_plan& plan, bool host);
+std::string jit_emit_source(const hq_group_plan& plan, bool host, bool zero_input = false);
 double jit_fp64_per_amp(const hq_group_plan& plan);
 int jit_min_blocks(int K);
 int jit_l2_prefetch_slots();
@@ -30,7 +30,7 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
 void jit_precompile(const std::string* identities, int n, const std::function<std::string(int)>& emit);
 bool jit_cached(const std::string& identity);
 void jit_release(JitKernel* k);   // the plan that fetched it is gone (unreferenced kernels may be evicted, 512 stay loaded)
-int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state);
+int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state, int amp0 = 0);
 int jit_max_blocks_per_sm(JitKernel* k, int block, size_t smem);
 void jit_stats(int* kernels, int* compiled, int* disk_hits, double* compile_seconds);
 bool jit_enabled();

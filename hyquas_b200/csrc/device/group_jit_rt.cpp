@@ -132,7 +132,7 @@ uint64_t fnv(const std::string& s, uint64_t h) {
     for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
     return h;
 }
-const char* kEmitterVersion = "hqjit3";   // bump when group_jit.cpp changes what it emits for the same plan
+const char* kEmitterVersion = "hqjit4";   // bump when group_jit.cpp changes what it emits for the same plan
 const char* kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "--ptxas-options=-v", "-lineinfo"};
 // `what` identifies the kernel: the bytes of the plan it is generated from (see plan_identity() in group_kernel.cu), so that a
 // cache hit costs a hash of ~20 KB and no source emission at all.  Compiler version, options and the emitter's version salt
@@ -380,9 +380,9 @@ void jit_release(JitKernel* k) {
     if (k->refs > 0) --k->refs;
 }
 
-int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state) {
+int jit_launch(JitKernel* k, int grid, int block, size_t smem, void* stream, void* state, int amp0) {
     Driver& d = driver();
-    void* args[] = {&state};
+    void* args[] = {&state, &amp0};
     const CUresult r = d.launchKernel(k->fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, (unsigned)smem, static_cast<CUstream>(stream), args, nullptr);
     if (r != CUDA_SUCCESS) {
         const char* s = nullptr;

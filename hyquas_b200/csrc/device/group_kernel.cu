@@ -824,6 +824,35 @@ static void resolve_jit(const hq_group_plan* plan) {
     plan->jit_occupancy = jit_max_blocks_per_sm(k, 2 * plan->NT, smem);
 }
 
+static void resolve_jit_zero(const hq_group_plan* plan) {
+    if (plan->jit_zero || plan->jit_zero_failed || plan->jit_identity_zero.empty()) return;
+    std::string why;
+    JitKernel* k = jit_get(plan->jit_identity_zero, jit_smem_bytes(plan->K), [&] { return jit_emit_source(*plan, false, true); }, &why);
+    if (!k) { plan->jit_zero_failed = true; return; }
+    plan->jit_zero = k;
+}
+
+// The first gate group of a circuit starts from |0...0>: its zero-input variant writes every tile without reading any and makes
+// the zero fill of the state unnecessary (one write sweep + one read sweep less per run).  Full-state plans only.
+extern "C" int hq_group_plan_enable_zero_input(hq_group_plan* plan) {
+    HQ_REQUIRE(plan != nullptr, "null plan");
+    if (plan->jit_identity.empty() || plan->fixed_mask != 0) return HQ_OK;   // interpreter-only or per-chunk plan: not available
+    plan->jit_identity_zero = plan->jit_identity + "|zero-input";
+    return HQ_OK;
+}
+
+// Launch on a state whose contents are irrelevant: the result is the group applied to |0...0> (has_amp0: this rank holds amplitude 0).
+// HQ_ERR_UNSUPPORTED when the variant is not available (the caller zero-fills and launches normally).
+extern "C" int hq_group_plan_launch_from_zero(const hq_group_plan* plan, void* state, int has_amp0) {
+    HQ_REQUIRE(plan != nullptr && state != nullptr, "null plan or state");
+    HQ_REQUIRE(rt().ready, "hq_init() has not been called");
+    resolve_jit_zero(plan);
+    if (!plan->jit_zero) { set_error("zero-input variant not available for this plan"); return HQ_ERR_UNSUPPORTED; }
+    const int occ = jit_max_blocks_per_sm(static_cast<JitKernel*>(plan->jit_zero), 2 * plan->NT, jit_smem_bytes(plan->K));
+    plan->grid = (int)std::min<uint64_t>((plan->p.ntiles + 1) / 2, (uint64_t)std::max(1, (rt().sm_count - rt().reserved_ctas) * occ));
+    return jit_launch(static_cast<JitKernel*>(plan->jit_zero), plan->grid, 2 * plan->NT, jit_smem_bytes(plan->K), rt().compute, state, has_amp0);
+}
+
 extern "C" int hq_group_plans_warm(hq_group_plan* const* plans, int n) {
     HQ_REQUIRE(n >= 0 && (n == 0 || plans != nullptr), "bad plan list");
     if (!rt().ready || !jit_enabled()) return HQ_OK;
@@ -834,8 +863,15 @@ extern "C" int hq_group_plans_warm(hq_group_plan* const* plans, int n) {
             ids.push_back(plans[i]->jit_identity);
             which.push_back(plans[i]);
         }
-    if (!ids.empty()) jit_precompile(ids.data(), (int)ids.size(), [&](int i) { return jit_emit_source(*which[i], false); });
-    for (int i = 0; i < n; ++i) if (plans[i]) resolve_jit(plans[i]);
+    std::vector<char> zero(ids.size(), 0);
+    for (int i = 0; i < n; ++i)
+        if (plans[i] && !plans[i]->jit_zero && !plans[i]->jit_zero_failed && !plans[i]->jit_identity_zero.empty() && !jit_cached(plans[i]->jit_identity_zero)) {
+            ids.push_back(plans[i]->jit_identity_zero);
+            which.push_back(plans[i]);
+            zero.push_back(1);
+        }
+    if (!ids.empty()) jit_precompile(ids.data(), (int)ids.size(), [&](int i) { return jit_emit_source(*which[i], false, zero[i] != 0); });
+    for (int i = 0; i < n; ++i) if (plans[i]) { resolve_jit(plans[i]); resolve_jit_zero(plans[i]); }
     return HQ_OK;
 }
 
@@ -915,6 +951,7 @@ extern "C" int hq_group_plan_destroy(hq_group_plan* plan) {
     if (!plan) return HQ_OK;
     if (plan->dev_blob) dev_free(plan->dev_blob);
     if (plan->jit) jit_release(static_cast<JitKernel*>(plan->jit));
+    if (plan->jit_zero) jit_release(static_cast<JitKernel*>(plan->jit_zero));
     delete plan;
     return HQ_OK;
 }

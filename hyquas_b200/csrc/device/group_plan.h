@@ -107,4 +107,8 @@ struct hq_group_plan {
     mutable void* jit = nullptr;          // hq::JitKernel*, resolved at the first launch (or by hq_group_plans_warm)
     mutable bool jit_failed = false;
     mutable int jit_occupancy = 0;
+    // zero-input variant (the launch's input is |0...0>: no HBM read, no prior zero fill), requested with hq_group_plan_enable_zero_input
+    std::string jit_identity_zero;
+    mutable void* jit_zero = nullptr;
+    mutable bool jit_zero_failed = false;
 };

@@ -36,7 +36,8 @@ public:
 
     // ---- extras used by the C-ABI / tests / bench -----------------------------------------------------------
     void prepareState();                                     // (re)allocate + |0..0>
-    int execute(std::vector<float>* perGroupMs = nullptr);   // the timed part of run() on the resident state
+    int execute(std::vector<float>* perGroupMs = nullptr, bool stateIsGarbage = false);   // the timed part of run() on the resident state
+    void allocState();                                       // allocate (and map to the peers) without initialising
     void destroyState();
     std::string stateDump();                                 // the text printState() prints
     bool fullState(std::vector<qComplex>& out);              // all 2^n amplitudes in LOGICAL order (single process, small n)

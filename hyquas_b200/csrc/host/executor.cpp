@@ -178,6 +178,11 @@ void Executor::prepare(Schedule& schedule, int numQubits, bool hostOnly) {
         for (auto& gg : lg.fullGroups) prepareGroup(gg, numQubits, {});
     }
     if (hostOnly) return;
+    // the very first launch of a run acts on |0...0>: ask for its zero-input variant (no zero fill, no read of the first sweep)
+    if (zeroInputEnabled() && !schedule.localGroups.empty() && !schedule.localGroups[0].fullGroups.empty()) {
+        GateGroup& first = schedule.localGroups[0].fullGroups[0];
+        if (first.backend != Backend::BLAS && first.plans.size() == 1) checkHq(hq_group_plan_enable_zero_input(static_cast<hq_group_plan*>(first.plans[0])));
+    }
     // tile-kernel groups run as per-group specialised kernels: fetch them from the cache, compiling the misses on all cores
     std::vector<hq_group_plan*> tilePlans;
     for (auto& lg : schedule.localGroups)
@@ -203,7 +208,31 @@ void Executor::release(Schedule& schedule) {
     }
 }
 
+bool Executor::zeroInputEnabled() {
+    static const bool on = !(getenv("HQ_ZERO_INPUT") && atoi(getenv("HQ_ZERO_INPUT")) == 0);
+    return on;
+}
+
+bool Executor::runFromZero() {
+    if (!zeroInputEnabled() || schedule.localGroups.empty() || schedule.localGroups[0].fullGroups.empty()) return false;
+    GateGroup& first = schedule.localGroups[0].fullGroups[0];
+    if (first.backend == Backend::BLAS || first.plans.size() != 1) return false;
+    if (perGroupMs) checkHq(hq_timer_start());
+    const int rc = hq_group_plan_launch_from_zero(static_cast<hq_group_plan*>(first.plans[0]), deviceStateVec[0], MyMPI::rank == 0);
+    if (rc == HQ_ERR_UNSUPPORTED) return false;   // nothing was launched
+    checkHq(rc);
+    if (perGroupMs) {
+        float ms = 0;
+        checkHq(hq_timer_stop_ms(&ms));
+        perGroupMs->push_back(ms);
+    }
+    firstFromZero = true;
+    run();
+    return true;
+}
+
 void Executor::applyGateGroup(GateGroup& gg, int chunk) {
+    if (firstFromZero && &gg == &schedule.localGroups[0].fullGroups[0]) { firstFromZero = false; return; }   // already done by runFromZero
     if (perGroupMs) checkHq(hq_timer_start());
     auto launch = [&](void* plan, qComplex* base) {
         if (gg.backend == Backend::BLAS) checkHq(hq_dense_plan_launch(static_cast<hq_dense_plan*>(plan), base, 0))

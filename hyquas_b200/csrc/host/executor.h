@@ -15,6 +15,10 @@ class Executor {
 public:
     Executor(std::vector<qComplex*> deviceStateVec, int numQubits, Schedule& schedule);
     void run();
+    // The state holds garbage and must become (schedule applied to |0...0>): the first gate group runs as its zero-input variant,
+    // which reads nothing; false when that variant is unavailable (the caller zero-fills and calls run()).
+    bool runFromZero();
+    static bool zeroInputEnabled();
     std::vector<float>* perGroupMs = nullptr;   // when set: one CUDA-event timing per gate-group launch (MEASURE_STAGE)
     static void prepare(Schedule& schedule, int numQubits, bool hostOnly = false);   // build device plans (idempotent)
     static void release(Schedule& schedule);                  // destroy device plans
@@ -23,6 +27,7 @@ public:
     static bool lowerGate(const Gate& gate, const State& state, qindex fixedMask, qindex fixedValue, hq_gate& out);
 private:
     void applyGateGroup(GateGroup& gg, int chunk);
+    bool firstFromZero = false;
     void finalize();
     std::vector<qComplex*> deviceStateVec;
     int numQubits;

@@ -95,6 +95,11 @@ int hq_group_plan_destroy(hq_group_plan* plan);
  * schedule's plans at once compiles the cache misses on all host cores. */
 /* what the specialised kernel of this plan costs: register rounds and FP64 instructions per amplitude (works host-only) */
 int hq_group_plan_cost(const hq_group_plan* plan, int* rounds, double* fp64_per_amp);
+/* The first group of a circuit acts on |0...0>: its zero-input variant reads nothing and needs no zero-filled state (kernelInit's
+ * memset + the first sweep's read, src/kernelSimple.cu:9-37).  enable before hq_group_plans_warm; launch_from_zero returns
+ * HQ_ERR_UNSUPPORTED when the variant is unavailable (zero-fill and launch normally then). */
+int hq_group_plan_enable_zero_input(hq_group_plan* plan);
+int hq_group_plan_launch_from_zero(const hq_group_plan* plan, void* state, int has_amp0);
 int hq_group_plans_warm(hq_group_plan* const* plans, int n);
 int hq_group_plan_is_specialised(const hq_group_plan* plan, int* yes);
 int hq_jit_available(int* yes);   /* HQ_JIT not 0 and NVRTC loadable; the evaluator prices tile groups accordingly */

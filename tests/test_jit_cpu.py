@@ -33,23 +33,24 @@ def random_state(n, seed):
     return s / np.linalg.norm(s)
 
 
-def jit_source(plan, host):
+def jit_source(plan, host, zero_input=False):
+    flavour = int(host) | (2 if zero_input else 0)
     need = ctypes.c_size_t()
-    check(lib.hq_debug_group_plan_jit_source(plan, int(host), None, 0, ctypes.byref(need)))
+    check(lib.hq_debug_group_plan_jit_source(plan, flavour, None, 0, ctypes.byref(need)))
     buf = ctypes.create_string_buffer(need.value)
-    check(lib.hq_debug_group_plan_jit_source(plan, int(host), buf, need.value, ctypes.byref(need)))
+    check(lib.hq_debug_group_plan_jit_source(plan, flavour, buf, need.value, ctypes.byref(need)))
     return buf.value.decode()
 
 
-def run_host_flavour(src, state):
+def run_host_flavour(src, state, amp0=0):
     with tempfile.TemporaryDirectory() as d:
         cpp, so = os.path.join(d, "k.cpp"), os.path.join(d, "k.so")
         open(cpp, "w").write(src)
         # -ffp-contract=off: the host build must not fuse what the source does not fuse
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", cpp, "-o", so])
         k = ctypes.CDLL(so)
-        k.hq_group_jit_host.argtypes = [ctypes.c_void_p]
-        k.hq_group_jit_host(state.ctypes.data)
+        k.hq_group_jit_host.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        k.hq_group_jit_host(state.ctypes.data, amp0)
 
 
 def make_plan(n, mask, gates):
@@ -154,3 +155,40 @@ def test_block_fusion_shortens_su4_blocks_and_keeps_amplitudes():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, HQ_JIT_NO_FUSE="1"), timeout=120)
     assert r.returncode == 0, r.stderr[-500:]
     assert fused < 0.8 * int(r.stdout.strip())
+
+
+@pytest.mark.parametrize("n,K,amp0", [(13, 10, 1), (14, 12, 1), (15, 12, 0)])
+def test_zero_input_variant_needs_no_initialised_state(n, K, amp0):
+    """The first group of a circuit acts on |0...0>: its zero-input variant reads nothing.  Run on a state full of garbage it must
+    produce the group applied to |0...0> (amp0 = 1: this rank holds amplitude 0) or to the zero vector (amp0 = 0: another rank does)."""
+    rng = random.Random(n)
+    rest = list(range(3, n))
+    rng.shuffle(rest)
+    tile = [0, 1, 2] + sorted(rest[:K - 3])
+    mask = sum(1 << b for b in tile)
+    _, gates = O.parse_qasm(C.random_circuit(n, 120, n))
+    keep = [g for g in gates if (g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target in tile]
+    plan = make_plan(n, mask, keep)
+    st = random_state(n, 77) * 1e3                      # garbage the kernel must never look at
+    run_host_flavour(jit_source(plan, True, zero_input=True), st, amp0)
+    lib.hq_group_plan_destroy(plan)
+    want = np.zeros(1 << n, dtype=np.complex128)
+    want[0] = float(amp0)
+    O.apply(want, n, keep)
+    assert np.max(np.abs(st - want)) < 1e-13
+
+
+def test_zero_input_cuda_flavour_compiles(tmp_path):
+    _, gates = O.parse_qasm(C.supremacy(14, cycles=8, seed=2))
+    keep = [g for g in gates if (g.mat[0, 1] == 0 and g.mat[1, 0] == 0) or g.target < 12]
+    plan = make_plan(14, 0xFFF, keep)
+    src = jit_source(plan, False, zero_input=True)
+    lib.hq_group_plan_destroy(plan)
+    assert "HQ_ZERO_INPUT" in src and "cp.async.bulk" in src      # (the prologue text is shared; the variant's kernel body issues no loads)
+    log = ctypes.create_string_buffer(1 << 16)
+    rc = lib.hq_debug_jit_compile_to_file(src.encode(), str(tmp_path / "z.cubin").encode(), log, len(log))
+    if rc != 0 and b"libnvrtc not found" in log.value:
+        pytest.skip("NVRTC not installed on this machine")
+    assert rc == 0, log.value.decode()[:2000]
+    sass = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "z.cubin")], capture_output=True, text=True).stdout
+    assert "UBLKCP" not in sass and "STG" in sass
