@@ -7,7 +7,9 @@
 
 Replaces evaluator-preprocess/process.cpp + benchmark/preprocess.sh of the reference (V100 tables, src/evaluator.h:18-117).
 Model (ms per 2^30 amplitudes, scaled by 2^(L-30)):
-    tile-kernel launch  = max(sweep, group_base + sum(gate cost) + round * extra rounds)
+    tile-kernel launch  = max(sweep, group_base + sum(gate cost) + round * extra rounds)            (interpreter kernel, HQ_JIT=0)
+                        = max(sweep + 0.015 I, 0.3 + instr * (I + 2 R) + jit_round * (R - 1))          (specialised kernels; I = FP64
+                          instructions per amplitude, R = register rounds; see host/evaluator.cpp)
     dense launch        = max(sweep, dense_base + sum(matrix cost[m]))
 """
 import json
@@ -37,11 +39,19 @@ def main():
         for t in types:
             print(f"gate {GATE_TYPES.index(t)} {cost:.4f}")
     # controlled rotations: no dedicated case -> general-mask bodies cost about an uncontrolled rotation
-    rx = (c["rx_x64_4q"]["ms_total"] * scale - base) / 64
-    for t in ("CRX", "CRY", "CRZ", "RY"):
-        print(f"gate {GATE_TYPES.index(t)} {rx * (0.75 if t != 'RY' else 0.8):.4f}")
+    if "rx_x64_4q" in c:   # (a --only run of the microbenchmark may have skipped it)
+        rx = (c["rx_x64_4q"]["ms_total"] * scale - base) / 64
+        for t in ("CRX", "CRY", "CRZ", "RY"):
+            print(f"gate {GATE_TYPES.index(t)} {rx * (0.75 if t != 'RY' else 0.8):.4f}")
     extra = (c["h_x96_12q"]["ms_total"] * scale - base - 96 * h_cost) / 2.0
     print(f"round_ms30 {max(extra, 0.0):.3f}")
+    # specialised (JIT) tile kernels, structural model: ms per FP64 instruction per amplitude (H = 2, U3 = 6 instructions per
+    # amplitude) from the long single-round cases; one extra round from the 12-qubit case (3 rounds)
+    instr = h256 / (256 * 2.0)
+    if "u3_x64_4q" in c:
+        instr = max(instr, c["u3_x64_4q"]["ms_total"] * scale / (64 * 6.0))
+    print(f"instr_ms30 {instr:.4f}")
+    print(f"jit_round_ms30 {max(0.0, (c['h_x96_12q']['ms_total'] * scale - 96 * 2.0 * instr) / 2.0):.3f}")
     dn = d.get("dense", {})
     if dn:
         m = {k: v["ms"] * scale for k, v in dn.items()}
