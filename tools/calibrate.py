@@ -51,7 +51,9 @@ def main():
     if "u3_x64_4q" in c:
         instr = max(instr, c["u3_x64_4q"]["ms_total"] * scale / (64 * 6.0))
     print(f"instr_ms30 {instr:.4f}")
-    print(f"jit_round_ms30 {max(0.0, (c['h_x96_12q']['ms_total'] * scale - 96 * 2.0 * instr) / 2.0):.3f}")
+    jr = (c["h_x96_12q"]["ms_total"] * scale - 96 * 2.0 * instr) / 2.0
+    if jr > 0.1:   # an FP64-bound case hides the exchange cost: keep the evaluator's default (0.9, from supremacy_30 launches) then
+        print(f"jit_round_ms30 {jr:.3f}")
     dn = d.get("dense", {})
     if dn:
         m = {k: v["ms"] * scale for k, v in dn.items()}
