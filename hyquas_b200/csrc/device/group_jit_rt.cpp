@@ -4,10 +4,11 @@
 // cudaGetDriverEntryPoint, so the library still loads on a machine without either (CPU tests; the product path then keeps
 // the interpreter kernel of group_kernel.cu -- still this library's CUDA path, never a CPU fallback).
 //
-// Cache: key = 128-bit content hash of (source, options, NVRTC version).  Hits in the process-wide map cost nothing; hits on
-// disk ($HQ_JIT_CACHE, else $XDG_CACHE_HOME/hyquas_b200/jit, else ~/.cache/hyquas_b200/jit, else /tmp/hyquas_b200_jit_<uid>)
-// cost a file read + cuModuleLoadData; misses cost one NVRTC compile (0.3-3 s for 20-150 gates), done on all host cores
-// when a whole schedule is prepared at once (jit_precompile).  The role of the reference's process-global cuTT plan cache
+// Cache: key = 128-bit hash of (the plan's identity bytes, compile options, NVRTC version, emitter version, kernel skeleton
+// text) -- the source itself is only emitted on a miss.  Hits in the process-wide map cost nothing; hits on disk ($HQ_JIT_CACHE,
+// else $XDG_CACHE_HOME/hyquas_b200/jit, else ~/.cache/hyquas_b200/jit, else /tmp/hyquas_b200_jit_<uid>) cost a file read +
+// cuModuleLoadData; misses cost one NVRTC compile (0.1-3 s for 20-150 gates), done on all host cores when a whole schedule is
+// prepared at once (jit_precompile).  A cached file the driver refuses to load is deleted and compiled again.  The role of the reference's process-global cuTT plan cache
 // (src/schedule.cpp:723-783), for kernels instead of transpose plans.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -138,8 +139,13 @@ const char* kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-
 // cache hit costs a hash of ~20 KB and no source emission at all.  Compiler version, options and the emitter's version salt
 // are part of the key.
 Key key_of(const std::string& what) {
-    std::string salt = std::string(kEmitterVersion) + "|" + std::to_string(nvrtc().major) + "." + std::to_string(nvrtc().minor);
-    for (const char* o : kOptions) salt += std::string("|") + o;
+    static const std::string salt = [] {
+        std::string t = std::string(kEmitterVersion) + "|" + std::to_string(nvrtc().major) + "." + std::to_string(nvrtc().minor);
+        for (const char* o : kOptions) t += std::string("|") + o;
+        // the skeleton every kernel is generated around: an edit there invalidates old cubins without a version bump
+        t += "|" + std::to_string(fnv(jit_device_prologue(), 0xcbf29ce484222325ull));
+        return t;
+    }();
     Key k;
     k.a = fnv(what, fnv(salt, 0xcbf29ce484222325ull));
     k.b = fnv(what, fnv(salt, 0x9e3779b97f4a7c15ull) ^ what.size());
@@ -154,28 +160,30 @@ struct Cache {
     uint64_t clock = 0;
     size_t max_loaded = 512;   // loaded modules kept (HQ_JIT_MAX_LOADED)
     double compile_seconds = 0;
-    std::string dir;
-    bool dir_ready = false;
+    std::string dir;           // set once by cache_dir()
 };
 Cache& cache() { static Cache c; return c; }
 
+void init_cache_dir(Cache& c);
 const std::string& cache_dir() {
+    static std::once_flag once;
     Cache& c = cache();
-    if (c.dir_ready) return c.dir;
-    c.dir_ready = true;
+    std::call_once(once, [&] { init_cache_dir(c); });
+    return c.dir;
+}
+void init_cache_dir(Cache& c) {
     if (const char* e = getenv("HQ_JIT_MAX_LOADED")) c.max_loaded = (size_t)std::max(8, atoi(e));
     std::string base;
     if (const char* e = getenv("HQ_JIT_CACHE")) base = e;
     else if (const char* x = getenv("XDG_CACHE_HOME")) base = std::string(x) + "/hyquas_b200/jit";
     else if (const char* h = getenv("HOME")) base = std::string(h) + "/.cache/hyquas_b200/jit";
     else base = "/tmp/hyquas_b200_jit_" + std::to_string((int)getuid());
-    if (base == "off" || base == "0") return c.dir;   // memory cache only
+    if (base == "off" || base == "0") return;   // memory cache only
     std::string path;
     for (size_t i = 1; i <= base.size(); ++i)
         if (i == base.size() || base[i] == '/') { path = base.substr(0, i); mkdir(path.c_str(), 0700); }
     struct stat st;
     if (stat(base.c_str(), &st) == 0 && S_ISDIR(st.st_mode) && access(base.c_str(), W_OK) == 0) c.dir = base;
-    return c.dir;
 }
 
 std::string file_of(const Key& k) {
@@ -322,7 +330,7 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
         if (it != c.loaded.end()) { ++it->second->refs; it->second->last_use = ++c.clock; return it->second; }
     }
     std::vector<char> cubin;
-    bool have = false;
+    bool have = false, from_disk = false;
     {
         std::lock_guard<std::mutex> lock(c.mu);
         auto it = c.cubins.find(k);
@@ -331,13 +339,14 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
     if (!have && read_disk(k, cubin)) {
         std::lock_guard<std::mutex> lock(c.mu);
         ++c.disk_hits;
-        have = true;
+        have = from_disk = true;
     }
-    if (!have) {
+    auto build = [&]() {
         const std::string src = emit();
-        if (src.empty()) { if (why) *why = "the emitter rejected this plan"; return nullptr; }
-        if (!obtain_cubin(k, src, cubin, why)) return nullptr;
-    }
+        if (src.empty()) { if (why) *why = "the emitter rejected this plan"; return false; }
+        return obtain_cubin(k, src, cubin, why);
+    };
+    if (!have && !build()) return nullptr;
     auto fail = [&](CUresult r, const char* what) {
         const char* s = nullptr;
         d.getErrorString(r, &s);
@@ -347,6 +356,12 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
     cudaSetDevice(rt().device);   // make the primary context current on this thread
     auto* jk = new JitKernel();
     CUresult r = d.moduleLoadData(&jk->mod, cubin.data());
+    if (r != CUDA_SUCCESS && from_disk) {   // a damaged or foreign file in the cache directory: drop it and compile
+        unlink(file_of(k).c_str());
+        cubin.clear();
+        if (!build()) { delete jk; return nullptr; }
+        r = d.moduleLoadData(&jk->mod, cubin.data());
+    }
     if (r != CUDA_SUCCESS) { delete jk; return fail(r, "cuModuleLoadData"); }
     r = d.moduleGetFunction(&jk->fn, jk->mod, "hq_group_jit");
     if (r != CUDA_SUCCESS) { d.moduleUnload(jk->mod); delete jk; return fail(r, "cuModuleGetFunction"); }
@@ -357,6 +372,14 @@ JitKernel* jit_get(const std::string& identity, size_t dynamic_smem, const std::
     d.funcGetAttribute(&jk->spill_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, jk->fn);
     std::lock_guard<std::mutex> lock(c.mu);
     c.cubins.erase(k);
+    auto raced = c.loaded.find(k);
+    if (raced != c.loaded.end()) {   // another host thread loaded the same kernel meanwhile: keep theirs
+        d.moduleUnload(jk->mod);
+        delete jk;
+        ++raced->second->refs;
+        raced->second->last_use = ++c.clock;
+        return raced->second;
+    }
     jk->refs = 1;
     jk->last_use = ++c.clock;
     c.loaded[k] = jk;
