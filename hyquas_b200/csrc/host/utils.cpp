@@ -6,10 +6,12 @@
 
 #include <signal.h>
 #include <spawn.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cstring>
 #include <ctime>
 #include <fstream>
@@ -30,6 +32,13 @@ bool swapAnyBit = false;
 static int envInt(const char* key, int dflt) {
     const char* v = getenv(key);
     return v ? atoi(v) : dflt;
+}
+
+// ranks started by the launcher below; a signal that ends the launcher (timeout(1), a batch system) is passed on to them
+static volatile pid_t spawnedRanks[64];
+static volatile int numSpawnedRanks = 0;
+static void forwardSignal(int sig) {
+    for (int i = 0; i < numSpawnedRanks; i++) if (spawnedRanks[i] > 0) kill(spawnedRanks[i], sig);
 }
 
 // Launcher mode.  The reference's single-process build drives every visible GPU from one `./main file.qasm`
@@ -110,16 +119,23 @@ static void selfSpawnIfNeeded() {
     const std::string port = "MASTER_PORT=" + std::to_string(20000 + (int)(getpid() % 20000));
     const std::string run = "TORCHELASTIC_RUN_ID=hq" + std::to_string((long long)time(nullptr));
     std::vector<pid_t> kids;
+    for (int sig : {SIGTERM, SIGINT, SIGHUP}) {
+        struct sigaction sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.sa_handler = forwardSignal;
+        sigaction(sig, &sa, nullptr);
+    }
     for (int r = 0; r < n; r++) {
         const pid_t pid = spawn({"RANK=" + std::to_string(r), "LOCAL_RANK=" + std::to_string(r), "WORLD_SIZE=" + std::to_string(n),
-                                 "HQ_SPAWNED=1", port, run, "MASTER_ADDR=127.0.0.1"}, -1);
+                                 "HQ_SPAWNED=" + std::to_string((long)getpid()), port, run, "MASTER_ADDR=127.0.0.1"}, -1);
         if (pid < 0) { fprintf(stderr, "hyquas_b200: cannot start rank %d\n", r); for (pid_t k : kids) kill(k, SIGTERM); exit(1); }
         kids.push_back(pid);
+        if (numSpawnedRanks < 64) { spawnedRanks[numSpawnedRanks] = pid; numSpawnedRanks = numSpawnedRanks + 1; }
     }
     int worst = 0;
     for (pid_t k : kids) {
         int st = 0;
-        waitpid(k, &st, 0);
+        while (waitpid(k, &st, 0) < 0 && errno == EINTR) {}
         const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + (WIFSIGNALED(st) ? WTERMSIG(st) : 0);
         if (code != 0 && worst == 0) { worst = code; for (pid_t o : kids) if (o != k) kill(o, SIGTERM); }
     }
@@ -134,6 +150,11 @@ void init() {
         printf("%d\n", visible);
         fflush(stdout);
         _exit(0);
+    }
+    if (getenv("HQ_SPAWNED")) {   // a rank of the launcher: do not outlive it
+        prctl(PR_SET_PDEATHSIG, SIGTERM);
+        const int launcher = atoi(getenv("HQ_SPAWNED"));
+        if (launcher > 1 && (int)getppid() != launcher) _exit(1);   // it was gone before the line above took effect
     }
     selfSpawnIfNeeded();
     MyMPI::init();
