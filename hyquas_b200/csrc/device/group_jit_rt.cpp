@@ -447,6 +447,17 @@ extern "C" int hq_debug_jit_compile_to_file(const char* source, const char* path
     return out ? HQ_OK : HQ_ERR_ARG;
 }
 
+// The cache layer without a GPU (tests): the kernel named `identity` goes through jit_precompile with `source` as its text;
+// *compiled / *disk_hits are the process totals afterwards.  What jit_get adds on top is the module load.
+extern "C" int hq_debug_jit_cache_probe(const char* identity, const char* source, int* compiled, int* disk_hits) {
+    if (!identity || !source) { hq::set_error("null argument"); return HQ_ERR_ARG; }
+    if (!hq::nvrtc().ok()) { hq::set_error("libnvrtc not found"); return HQ_ERR_UNSUPPORTED; }
+    const std::string id = identity, src = source;
+    hq::jit_precompile(&id, 1, [&](int) { return src; });
+    hq::jit_stats(nullptr, compiled, disk_hits, nullptr);
+    return hq::jit_cached(id) ? HQ_OK : HQ_ERR_UNSUPPORTED;
+}
+
 // 1 when gate groups will run as specialised kernels: HQ_JIT not 0 and NVRTC loadable (no GPU needed to answer)
 extern "C" int hq_jit_available(int* yes) {
     if (yes) *yes = hq::jit_enabled() && hq::nvrtc().ok();

@@ -192,3 +192,47 @@ def test_zero_input_cuda_flavour_compiles(tmp_path):
     assert rc == 0, log.value.decode()[:2000]
     sass = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "z.cubin")], capture_output=True, text=True).stdout
     assert "UBLKCP" not in sass and "STG" in sass
+
+
+_CACHE_PROBE = r"""
+import ctypes, sys
+sys.path.insert(0, %(root)r)
+from hyquas_b200._lib import lib
+src = open(%(src)r).read().encode()
+comp, hits = ctypes.c_int(), ctypes.c_int()
+rc = lib.hq_debug_jit_cache_probe(%(ident)r, src, ctypes.byref(comp), ctypes.byref(hits))
+print(rc, comp.value, hits.value)
+"""
+
+
+def test_kernel_cache_compiles_once_then_reads_the_disk(tmp_path):
+    """The cache layer on its own (no GPU): a miss compiles and leaves <key>.cubin in $HQ_JIT_CACHE, a second process finds it there,
+    another identity misses, and a damaged file is not accepted as a hit."""
+    import subprocess
+    import sys
+    plan = make_plan(12, 0x3FF, [O.OGate("h", 8), O.OGate("cz", 8, 9), O.OGate("t", 9)])
+    src = jit_source(plan, False)
+    lib.hq_group_plan_destroy(plan)
+    (tmp_path / "k.cu").write_text(src)
+    cache = tmp_path / "cache" / "nested"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def probe(ident):
+        code = _CACHE_PROBE % {"root": root, "src": str(tmp_path / "k.cu"), "ident": ident}
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, HQ_JIT_CACHE=str(cache)), capture_output=True,
+                             text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [int(t) for t in out.stdout.split()[-3:]]
+
+    first = probe(b"plan-a")
+    if first[0] != 0:
+        pytest.skip("NVRTC not installed on this machine")
+    assert first == [0, 1, 0]
+    files = sorted(cache.glob("*.cubin"))
+    assert len(files) == 1 and files[0].read_bytes()[:4] == b"\x7fELF" and not list(cache.glob("*.tmp*"))
+    assert probe(b"plan-a") == [0, 0, 1]            # second process: no compile, one disk hit
+    assert probe(b"plan-b") == [0, 1, 0]            # the key follows the identity, not the source text
+    assert len(list(cache.glob("*.cubin"))) == 2
+    files[0].write_bytes(b"not a cubin")             # damaged entry: compiled again and replaced
+    assert probe(b"plan-a") == [0, 1, 0]
+    assert files[0].read_bytes()[:4] == b"\x7fELF"
