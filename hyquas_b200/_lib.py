@@ -66,6 +66,7 @@ _SIGS = {
     "hq_group_plans_warm": (_c.c_int, [_P(_c.c_void_p), _c.c_int]),
     "hq_group_plan_is_specialised": (_c.c_int, [_c.c_void_p, _P(_c.c_int)]),
     "hq_jit_available": (_c.c_int, [_P(_c.c_int)]),
+    "hq_cache_dir": (_c.c_int, [_c.c_char_p, _c.c_size_t]),
     "hq_jit_stats": (_c.c_int, [_P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_double)]),
     "hq_group_apply": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _P(HqGate), _c.c_int]),
     "hq_microbench_fp64": (_c.c_int, [_c.c_int, _P(_c.c_double)]),

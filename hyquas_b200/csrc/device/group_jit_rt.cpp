@@ -458,6 +458,15 @@ extern "C" int hq_debug_jit_cache_probe(const char* identity, const char* source
     return hq::jit_cached(id) ? HQ_OK : HQ_ERR_UNSUPPORTED;
 }
 
+// where this library keeps files between runs (compiled kernels, the partitioner's search results); empty = disk caching is off
+extern "C" int hq_cache_dir(char* out, size_t cap) {
+    if (!out || cap == 0) { hq::set_error("null argument"); return HQ_ERR_ARG; }
+    const std::string& d = hq::cache_dir();
+    if (d.size() + 1 > cap) { hq::set_error("buffer too small"); return HQ_ERR_ARG; }
+    std::memcpy(out, d.c_str(), d.size() + 1);
+    return HQ_OK;
+}
+
 // 1 when gate groups will run as specialised kernels: HQ_JIT not 0 and NVRTC loadable (no GPU needed to answer)
 extern "C" int hq_jit_available(int* yes) {
     if (yes) *yes = hq::jit_enabled() && hq::nvrtc().ok();

@@ -7,6 +7,7 @@
 // src/compiler.cpp:70-452); the algorithms are new (frontier scans with commutation-aware blocking and a
 // greedy qubit-gain search instead of the std::bitset reachability DP).
 #pragma once
+#include <unordered_map>
 #include <vector>
 
 #include "gate.h"
@@ -23,6 +24,7 @@ public:
     int pinnedBits;    // lowest physical bits always kept in the tile (contiguous-run length of HBM accesses)
     int maxGroupGates; // cap on gates per group
     bool rebalanceGroups; // adjacent tile groups trade gates to even out compute-bound and sweep-bound launches (HQ_REBALANCE)
+    int cutVariants;   // most differently seeded greedy cuts tried per stage; the cheapest predicted total wins (HQ_CUT_VARIANTS, 1 = off)
     bool cutBothWays;  // try the greedy cut from both ends of a stage, keep the cheaper predicted total
     bool enableOverlap; // per-chunk groups under the exchange (reference: ENABLE_OVERLAP)
     int backendMode;   // 1 = tile kernel only, 3 = dense kernel only, 4 = hybrid (reference: -DBACKEND=group|blas|mix)
@@ -37,7 +39,16 @@ private:
     std::vector<GateGroup> cutGroupsBothWays(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     void rebalance(std::vector<GateGroup>& groups, int nEff) const;
     void absorbCrumbs(std::vector<GateGroup>& groups, int nEff) const;
-    std::vector<GateGroup> cutGroupsGreedy(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
+    std::vector<GateGroup> cutGroupsGreedy(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude, int variant = 0,
+                                           bool tileOnly = false) const;
+    int trialsFor(size_t numGates) const;
+    unsigned long long cutKey(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
+    unsigned long long circuitKey() const;
+    void loadWisdom();
+    void saveWisdom() const;
+    // winning seed of every searched cut of this circuit (0 = the plain greedy cut), kept across compiles: see cutGroups
+    mutable std::unordered_map<unsigned long long, int> wisdom;
+    mutable bool wisdomDirty = false;
     int numQubits;
     int numLocal;
     std::vector<Gate> gates;

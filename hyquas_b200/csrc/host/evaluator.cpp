@@ -288,6 +288,21 @@ double Evaluator::perfPerGate(int numQubits, const std::vector<Gate>& gates) {
     return launchMs + std::ldexp(1.0, numQubits - 30) * std::max(sweepMs30(), compute);
 }
 
+unsigned long long Evaluator::signature(int numQubits) {
+    loadParam(numQubits);
+    unsigned long long h = 0xcbf29ce484222325ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
+    };
+    const double scalars[] = {nvlinkGBs, hbmGBs, groupBaseMs30, denseBaseMs30, roundMs30, circuitFactor, launchMs, instrMs30, jitRoundMs30,
+                              jitBaseMs30, jitUnderSweepMs30, specialised ? 1.0 : 0.0, fusionAware ? 1.0 : 0.0};
+    mix(scalars, sizeof(scalars));
+    mix(gateNs, sizeof(gateNs));
+    mix(denseMs30, sizeof(denseMs30));
+    return h;
+}
+
 double Evaluator::perfPerGate(int numQubits, const GateGroup* gg) { return perfPerGate(numQubits, gg->gates); }
 
 double Evaluator::perfDense(int numQubits, const std::vector<int>& ms) {

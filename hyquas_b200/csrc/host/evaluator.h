@@ -52,6 +52,7 @@ public:
     static double fusedInstr(const std::vector<Gate>& gates);    // instruction count if every one- / two-qubit block fuses
     bool fusionAware;                       // price tile groups with block fusion in mind (HQ_EVAL_FUSION=0 switches it off)
     static int registerRounds(const std::vector<Gate>& gates);   // rounds the tile kernel will need for this group
+    unsigned long long signature(int numQubits);                 // hash of every model constant in force for this size
 private:
     Evaluator();
     bool loaded = false;

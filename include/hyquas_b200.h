@@ -104,6 +104,9 @@ int hq_group_plans_warm(hq_group_plan* const* plans, int n);
 int hq_group_plan_is_specialised(const hq_group_plan* plan, int* yes);
 int hq_jit_available(int* yes);   /* HQ_JIT not 0 and NVRTC loadable; the evaluator prices tile groups accordingly */
 int hq_jit_stats(int* kernels_loaded, int* compiled, int* disk_hits, double* compile_seconds);
+/* directory of the on-disk caches (compiled kernels, partitioner search results): $HQ_JIT_CACHE, else
+ * $XDG_CACHE_HOME/hyquas_b200/jit, else ~/.cache/hyquas_b200/jit; "" when HQ_JIT_CACHE=off */
+int hq_cache_dir(char* out, size_t cap);
 int hq_group_apply(void* state, int L, uint64_t tile_mask, const hq_gate* gates, int ngates);   /* create+launch+destroy */
 
 /* ---- fused dense-matrix kernel (replaces the TransMM path: cuttExecute + cublasZgemm in Executor::applyBlasGroup,

@@ -195,3 +195,83 @@ def test_supremacy_30_schedule_stays_short_and_balanced():
     sweep = min(g["predicted_ms"] for g in groups)
     assert max(g["predicted_ms"] for g in groups) < 2.0 * sweep
     c.close()
+
+
+def _plan(name, world=1):
+    api.init_host_only(world, 0)
+    c = api.Circuit.from_qasm(C.generate(name))
+    c.compile()
+    groups = [(g["backend"], g["gates"], g["launches"], round(g["predicted_ms"], 6)) for g in c.groups()]
+    c.close()
+    return groups
+
+
+@pytest.mark.parametrize("name", ["supremacy_20", "qaoa_20", "supremacy_30", "qaoa_28"])
+def test_cut_search_never_loses_to_the_plain_cut_and_is_repeatable(monkeypatch, name):
+    """Differently seeded greedy cuts of a stage are compared by predicted time (HQ_CUT_VARIANTS trials at most, 1 = the plain cut
+    only): the schedule kept is never predicted slower than the plain one, and compiling again -- now replaying the remembered
+    seed instead of searching -- gives the same groups."""
+    monkeypatch.setenv("HQ_CUT_VARIANTS", "1")
+    plain = _plan(name)
+    monkeypatch.delenv("HQ_CUT_VARIANTS")
+    searched = _plan(name)
+    total = lambda gs: sum(g[3] * g[2] for g in gs)
+    assert total(searched) <= total(plain) + 1e-9
+    assert sum(g[1] for g in searched) == sum(g[1] for g in plain)      # the same gates, cut differently
+    assert _plan(name) == searched
+    if name == "supremacy_30":
+        assert len(searched) <= 9 and total(searched) < 0.95 * total(plain)
+
+
+def test_searched_schedules_reproduce_the_oracle(monkeypatch):
+    """A circuit whose search picks a seeded cut (not the plain one) still computes the oracle's amplitudes, and the one-pass
+    frontier scan agrees with the reference scan on every candidate it is asked about (HQ_CHECK_SCANS)."""
+    monkeypatch.setenv("HQ_CHECK_SCANS", "1")
+    picked = 0
+    for name in ["supremacy_18", "qaoa_18", "supremacy_20"]:
+        text = C.generate(name)
+        monkeypatch.setenv("HQ_CUT_VARIANTS", "1")
+        plain = _plan(name)
+        monkeypatch.delenv("HQ_CUT_VARIANTS")
+        n, got, info = emulate_circuit(text)
+        picked += _plan(name) != plain
+        _, gates = O.parse_qasm(text)
+        assert np.max(np.abs(got - O.simulate(n, gates))) < 1e-12
+    assert picked > 0
+
+
+_WISDOM_PROBE = r"""
+import sys, json
+sys.path.insert(0, %(root)r)
+from hyquas_b200 import api, circuits as C
+api.init_host_only(%(world)d, 0)
+c = api.Circuit.from_qasm(C.generate(%(name)r))
+c.compile()
+print(json.dumps([(g["backend"], g["gates"], g["launches"], round(g["predicted_ms"], 6)) for g in c.groups()]))
+"""
+
+
+@pytest.mark.parametrize("name,world", [("supremacy_20", 1), ("supremacy_22", 4)])
+def test_cut_search_results_are_kept_on_disk(tmp_path, name, world):
+    """The winning seeds go to <cache dir>/<circuit key>.cuts; a new process replays them and ends up with the same schedule as the
+    process that searched; a file full of nonsense is ignored."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HQ_JIT_CACHE=str(tmp_path / "cache"))
+    env.pop("HQ_CUT_VARIANTS", None)
+
+    def run():
+        out = subprocess.run([sys.executable, "-c", _WISDOM_PROBE % {"root": root, "name": name, "world": world}], env=env,
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    first = run()
+    files = list((tmp_path / "cache").glob("*.cuts"))
+    assert len(files) == 1 and files[0].read_text().strip()
+    assert run() == first
+    files[0].write_text("zzzz not a table\n12 99999\n")
+    assert run() == first
