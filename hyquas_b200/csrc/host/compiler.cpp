@@ -607,7 +607,8 @@ void Compiler::saveWisdom() const {
     if (!ok || rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str());
 }
 
-std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal, qindex exclude) const {
+std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, const State& state, int nLocal, qindex exclude,
+                                           bool search) const {
     const int nEff = nLocal - bitCount(exclude);
     auto finish = [&](std::vector<GateGroup>& out) {
         rebalance(out, nEff);
@@ -616,7 +617,7 @@ std::vector<GateGroup> Compiler::cutGroups(const std::vector<Gate>& stageGates, 
         if (out.size() != before) rebalance(out, nEff);
     };
     auto total = [](const std::vector<GateGroup>& gs) { double t = 0; for (auto& g : gs) t += g.predictedMs; return t; };
-    const int V = trialsFor(stageGates.size());
+    const int V = search ? trialsFor(stageGates.size()) : 1;
     const unsigned long long key = V > 1 ? cutKey(stageGates, state, nLocal, exclude) : 0;
     int known = -1;
     if (V > 1) {
@@ -828,7 +829,9 @@ Schedule Compiler::run() {
         std::vector<Gate> tailGates;
         for (int gi : tail) tailGates.push_back(prev[gi]);
         if (tailGates.empty()) continue;
-        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude);
+        // (the plain cut here: which gates CAN be deferred should not depend on seeds, so that every option below is the plain
+        // pipeline's option with its full groups cut at least as well)
+        std::vector<GateGroup> cand = cutGroups(tailGates, lg.state, numLocal, exclude, false);
         const State& prevState = schedule.localGroups[s - 1].state;
         // Per-chunk launches leave 32 of 148 SMs and some HBM bandwidth to the exchange kernel.  Measured (r02_m8, supremacy_33:
         // 1/8-state launches of 6.3 ms groups take 1.25 ms, not 0.79) the slowdown is ~1.5; the chooser was measured with 1.3
@@ -850,8 +853,10 @@ Schedule Compiler::run() {
         };
         // every candidate costs one cut of stage s-1 (milliseconds of compile time): the cut that wins is kept for pass 3, and at
         // most four deferral depths are tried
+        static const bool verbosePlan = getenv("HQ_PLAN_VERBOSE") != nullptr;   // developer aid: the options weighed below
         std::vector<GateGroup> bestCut = cutGroups(prev, prevState, numLocal, 0);
         double bestCost = total(bestCut) + commMs;
+        if (verbosePlan) fprintf(stderr, "[hq plan] stage %zu: no deferral: %zu groups %.2f ms + exchange %.2f ms\n", s, bestCut.size(), total(bestCut), commMs);
         size_t bestFirst = cand.size();
         double deferredMs = 0;
         for (size_t first = cand.size(); first-- > 0 && cand.size() - first <= 4;) {
@@ -864,6 +869,9 @@ Schedule Compiler::run() {
             for (auto& g : prev) if (!std::binary_search(ids.begin(), ids.end(), g.gateID)) rest.push_back(g);
             std::vector<GateGroup> cut = cutGroups(rest, prevState, numLocal, 0);
             const double cost = total(cut) + pipelined(deferredMs);
+            if (verbosePlan)
+                fprintf(stderr, "[hq plan] stage %zu: deferring %zu group(s): rest %zu groups %.2f ms + pipelined(%.2f) = %.2f -> %.2f ms; best so far %.2f\n",
+                        s, cand.size() - first, cut.size(), total(cut), deferredMs, pipelined(deferredMs), cost, bestCost);
             // (a huge HQ_OVERLAP_SLACK forces the maximal deferral whatever it costs: tests of the per-chunk path at sizes
             // whose exchange is too short to be worth hiding)
             if (cost < bestCost - 1e-9 || overlapSlack > 1e6) { bestCost = cost; bestFirst = first; bestCut.swap(cut); }

@@ -35,7 +35,7 @@ private:
     std::vector<Stage> splitStages() const;
     std::vector<Stage> splitStagesVariant(int variant) const;
     GateGroup denseCandidate(const std::vector<Gate>& gates, const std::vector<int>& remaining, const State& state, int numLocal, qindex exclude) const;
-    std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
+    std::vector<GateGroup> cutGroups(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude, bool search = true) const;
     std::vector<GateGroup> cutGroupsBothWays(const std::vector<Gate>& gates, const State& state, int numLocal, qindex exclude) const;
     void rebalance(std::vector<GateGroup>& groups, int nEff) const;
     void absorbCrumbs(std::vector<GateGroup>& groups, int nEff) const;
