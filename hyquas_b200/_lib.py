@@ -131,6 +131,7 @@ _SIGS = {
     "hq_debug_jit_compile_to_file": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_size_t]),
     "hq_debug_jit_cache_probe": (_c.c_int, [_c.c_char_p, _c.c_char_p, _P(_c.c_int), _P(_c.c_int)]),
     "hq_debug_dense_plan_emulate": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "hq_debug_schedule_check": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t]),
     "hq_debug_num_stages": (_c.c_int, [_c.c_void_p]),
     "hq_debug_stage_swap": (_c.c_int, [_c.c_void_p, _c.c_int, _P(_c.c_int), _P(_c.c_int), _P(_c.c_int), _P(_c.c_int),
                                        _P(_c.c_int), _P(_c.c_int), _P(_c.c_int)]),

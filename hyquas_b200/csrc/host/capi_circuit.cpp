@@ -118,6 +118,33 @@ extern "C" int hq_circuit_plan_only(hq_circuit* h, int* stages, int* groups, int
     return HQ_OK;
 }
 
+// Test hook: partition the circuit as compile() would and check the schedule against the gate list (hyquas::checkSchedule);
+// HQ_OK and an empty message when it is a valid reordering.  Works without a GPU (plan only, nothing is lowered or uploaded).
+extern "C" int hq_debug_schedule_check(hq_circuit* h, char* why, size_t cap) {
+    if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
+    g_cerr = h->c->compileError();
+    if (!g_cerr.empty()) return HQ_ERR_ARG;
+    const std::vector<Gate> gates = hyquas::peephole(h->c->getGates(), nullptr);
+    Compiler compiler(h->c->numQubits, gates);
+    Schedule s = compiler.run();
+    if (const char* e = getenv("HQ_TEST_BREAK_SCHEDULE")) {   // (the tests of the checker itself: damage the schedule first)
+        std::vector<GateGroup>& first = s.localGroups.front().fullGroups;
+        std::vector<GateGroup>& last = s.localGroups.back().fullGroups;
+        if (!first.empty() && !last.empty() && !last.back().gates.empty()) {
+            if (atoi(e) == 1) first.front().gates.insert(first.front().gates.begin(), last.back().gates.back());   // a gate twice
+            else if (atoi(e) == 2) last.back().gates.pop_back();                                                   // a gate missing
+            else if (atoi(e) == 3) std::swap(first.front().gates, last.back().gates);                              // tiles
+            else std::reverse(first.front().gates.begin(), first.front().gates.end());                             // order
+        }
+    }
+    std::vector<Gate> numbered = gates;
+    for (size_t i = 0; i < numbered.size(); i++) numbered[i].gateID = (int)i;   // the ids the Compiler gave its copy
+    const std::string bad = hyquas::checkSchedule(s, numbered, h->c->numQubits, h->c->numQubits - MyGlobalVars::bit, compiler.tileBits);
+    if (why && cap) snprintf(why, cap, "%s", bad.c_str());
+    if (!bad.empty()) { g_cerr = bad; return HQ_ERR_UNSUPPORTED; }
+    return HQ_OK;
+}
+
 extern "C" int hq_circuit_run(hq_circuit* h, int copy_back, int destroy, int* time_us, double* device_ms) {
     if (!h) { g_cerr = "null circuit"; return HQ_ERR_ARG; }
     const int us = h->c->run(copy_back != 0, destroy != 0);

@@ -898,3 +898,60 @@ Schedule Compiler::run() {
     saveWisdom();
     return schedule;
 }
+
+namespace hyquas {
+// Independent check of a schedule against the gate list it was cut from (tests; works without a GPU).  The launches, in the order
+// the executor issues them (per stage: the per-chunk groups under the incoming exchange, then the full groups), must hold every
+// gate exactly once, keep the relative order of every pair of gates that does not commute, and give every non-diagonal gate a
+// target that is local in its stage, inside the launch's tile, and -- for per-chunk groups -- off the positions being exchanged.
+std::string checkSchedule(const Schedule& schedule, const std::vector<Gate>& gates, int numQubits, int numLocal, int tileBits) {
+    char msg[256];
+    std::vector<int> where(gates.size(), -1);   // gate id -> position in the launch order
+    int next = 0, stage = 0;
+    for (const LocalGroup& lg : schedule.localGroups) {
+        qindex swapped = 0;
+        for (int b : lg.swap.localBit) swapped |= qindex(1) << b;
+        int which = 0;
+        for (const std::vector<GateGroup>* groups : {&lg.overlapGroups, &lg.fullGroups}) {
+            const bool perChunk = which++ == 0;
+            for (const GateGroup& gg : *groups) {
+                if (gg.backend == Backend::PerGate && bitCount(gg.relatedQubits) > tileBits) return "a tile of more than tileBits qubits";
+                qindex blockQubits = 0;
+                for (const DenseBlock& b : gg.blocks) blockQubits |= b.qubits;
+                for (const Gate& g : gg.gates) {
+                    if (g.gateID < 0 || g.gateID >= (int)gates.size()) return "a gate id outside the circuit";
+                    if (where[g.gateID] >= 0) { snprintf(msg, sizeof(msg), "gate %d is scheduled twice", g.gateID); return msg; }
+                    where[g.gateID] = next++;
+                    qindex need = g.isDiagonal() ? 0 : qindex(1) << g.targetQubit;   // qubits that must be movable in this launch
+                    if (gg.backend == Backend::BLAS) {
+                        need |= qindex(1) << g.targetQubit;
+                        if (g.controlQubit >= 0) need |= qindex(1) << g.controlQubit;
+                        if (g.controlQubit2 >= 0) need |= qindex(1) << g.controlQubit2;
+                        if (need & ~blockQubits) { snprintf(msg, sizeof(msg), "gate %d reaches outside its dense blocks", g.gateID); return msg; }
+                    } else if (need & ~gg.relatedQubits) {
+                        snprintf(msg, sizeof(msg), "stage %d: target of gate %d is not in its launch's tile", stage, g.gateID);
+                        return msg;
+                    }
+                    for (int q = 0; q < numQubits; q++) {
+                        if (!(need >> q & 1)) continue;
+                        const int p = lg.state.pos[q];
+                        if (p >= numLocal) { snprintf(msg, sizeof(msg), "stage %d: gate %d needs qubit %d, which is global", stage, g.gateID, q); return msg; }
+                        if (perChunk && (swapped >> p & 1)) { snprintf(msg, sizeof(msg), "stage %d: per-chunk gate %d needs a position under exchange", stage, g.gateID); return msg; }
+                    }
+                }
+            }
+        }
+        stage++;
+    }
+    for (size_t i = 0; i < gates.size(); i++)
+        if (where[i] < 0) { snprintf(msg, sizeof(msg), "gate %zu is not scheduled", i); return msg; }
+    for (size_t j = 0; j < gates.size(); j++)
+        for (size_t i = 0; i < j; i++)
+            if (where[i] > where[j] && !gatesCommute(gates[i], gates[j])) {
+                snprintf(msg, sizeof(msg), "gates %zu and %zu do not commute but run in the opposite order", i, j);
+                return msg;
+            }
+    return std::string();
+}
+}  // namespace hyquas
+

@@ -7,6 +7,7 @@
 // src/compiler.cpp:70-452); the algorithms are new (frontier scans with commutation-aware blocking and a
 // greedy qubit-gain search instead of the std::bitset reachability DP).
 #pragma once
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -60,5 +61,8 @@ namespace hyquas {
 // non-diagonal targets?  Gates that cannot run block later gates they do not commute with.
 std::vector<int> runnableGates(const std::vector<Gate>& gates, const std::vector<int>& order, qindex tileSet, int cap);
 std::vector<int> runnableDense(const std::vector<Gate>& gates, const std::vector<int>& order, qindex qset, int cap);
+// "" when `schedule` is a valid way to run `gates` (every gate once, non-commuting pairs in order, targets local / in tile / off
+// the exchanged positions), else what is wrong with it
+std::string checkSchedule(const Schedule& schedule, const std::vector<Gate>& gates, int numQubits, int numLocal, int tileBits);
 hyquas::SwapPlan planSwap(State& state, qindex newLocals, int numQubits, int numLocal, bool anyBit);
 }

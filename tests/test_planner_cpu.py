@@ -275,3 +275,32 @@ def test_cut_search_results_are_kept_on_disk(tmp_path, name, world):
     assert run() == first
     files[0].write_text("zzzz not a table\n12 99999\n")
     assert run() == first
+
+
+def _check_schedule(name, world):
+    api.init_host_only(world, 0)
+    c = api.Circuit.from_qasm(C.generate(name))
+    why = ctypes.create_string_buffer(512)
+    rc = lib.hq_debug_schedule_check(c._h, why, len(why))
+    c.close()
+    return rc, why.value.decode()
+
+
+@pytest.mark.parametrize("world,name", [(1, "supremacy_30"), (2, "supremacy_31"), (4, "supremacy_32"), (8, "supremacy_33"),
+                                        (1, "qaoa_30"), (4, "qaoa_34"), (8, "qaoa_34"), (1, "quantum_volume_30"), (1, "qft_28"),
+                                        (8, "bv_36"), (8, "hidden_shift_36"), (8, "adder_36"), (8, "qft_36"),
+                                        (8, "quantum_volume_33")])
+def test_full_size_benchmark_schedules_are_valid_reorderings(world, name):
+    """BASELINE.json's configurations at FULL size (no state is allocated: plan only): the launches, in execution order, hold every
+    gate exactly once, never swap two gates that do not commute, and every non-diagonal target is local, inside its launch's tile
+    and -- for per-chunk groups -- off the positions under exchange.  The amplitudes of these schedules are checked on the GPU; this
+    is the part of that check that needs no GPU."""
+    rc, why = _check_schedule(name, world)
+    assert rc == 0, why
+
+
+@pytest.mark.parametrize("damage,expect", [("1", "twice"), ("2", "not scheduled"), ("3", "tile"), ("4", "opposite order")])
+def test_schedule_checker_sees_damage(monkeypatch, damage, expect):
+    monkeypatch.setenv("HQ_TEST_BREAK_SCHEDULE", damage)
+    rc, why = _check_schedule("supremacy_20", 1)
+    assert rc != 0 and expect in why, why
