@@ -1,5 +1,6 @@
 // Circuit-level C-ABI (declared in include/hyquas_b200_circuit.h): lets non-C++ hosts (the ctypes tests,
 // bench.py) drive exactly the code path `hyquas_main` runs: parse / addGate -> compile -> run -> dump.
+#include <algorithm>
 #include <cstring>
 #include <memory>
 
