@@ -236,3 +236,40 @@ def test_kernel_cache_compiles_once_then_reads_the_disk(tmp_path):
     files[0].write_bytes(b"not a cubin")             # damaged entry: compiled again and replaced
     assert probe(b"plan-a") == [0, 1, 0]
     assert files[0].read_bytes()[:4] == b"\x7fELF"
+
+
+_DUMP_KERNELS = r"""
+import sys
+sys.path.insert(0, %(root)r)
+from hyquas_b200 import api, circuits as C
+api.init_host_only(%(world)d, 0)
+c = api.Circuit.from_qasm(C.generate(%(name)r))
+c.compile()
+print(len(c.groups()))
+"""
+
+
+@pytest.mark.parametrize("name,world", [("supremacy_30", 1), ("supremacy_31", 2)])
+def test_every_kernel_of_the_headline_schedule_compiles_within_the_register_budget(tmp_path, name, world):
+    """The schedule bench.py times (rank 0's share of it): every gate group's specialised kernel is emitted (HQ_JIT_DUMP_DIR, no GPU
+    needed) and compiled for sm_100a here; none may fall back to the interpreter kernel on the GPU box because NVRTC rejects it,
+    and none may spill its working set (512 threads per CTA: 128 registers)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _DUMP_KERNELS % {"root": root, "name": name, "world": world}],
+                         env=dict(os.environ, HQ_JIT_DUMP_DIR=str(tmp_path)), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    sources = sorted(tmp_path.glob("group_*.cu"))
+    assert len(sources) >= int(out.stdout.split()[-1])
+    log = ctypes.create_string_buffer(1 << 16)
+    for src in sources:
+        rc = lib.hq_debug_jit_compile_to_file(src.read_bytes(), str(src.with_suffix(".cubin")).encode(), log, len(log))
+        if rc != 0 and b"libnvrtc not found" in log.value:
+            pytest.skip("NVRTC not installed on this machine")
+        info = log.value.decode()
+        assert rc == 0, (src.name, info[:2000])
+        m = re.search(r"Used (\d+) registers", info)
+        assert m and int(m.group(1)) <= 128, (src.name, info)
+        sp = re.search(r"(\d+) bytes spill stores", info)
+        assert sp is None or int(sp.group(1)) <= 512, (src.name, info)
