@@ -15,3 +15,12 @@ print("ms", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["ms_per_step"
 print([(g["gates"], g["ms"], g["predicted_ms"]) for g in d["groups"]])
 P
 echo "== hyquas_main, single GPU, golden"; ./hyquas_b200/hyquas_main tests/golden/bv_28.qasm 2>/dev/null | grep -v Logger | diff -q - tests/golden/bv_28.log && echo "bv_28 golden identical"
+echo "== cut search A/B through the CLI (supremacy_30, plain vs searched cut; r02_s13)"
+python -c "
+import sys; sys.path.insert(0, '.')
+from hyquas_b200 import circuits as C
+open('$O/s30.qasm', 'w').write(C.supremacy(30))"
+for v in 1 32; do for i in 1 2; do
+  HQ_NUM_GPUS=1 HQ_CUT_VARIANTS=$v ./hyquas_b200/hyquas_main $O/s30.qasm > $O/cli_v${v}_$i.out 2> $O/cli_v${v}_$i.err
+  echo "HQ_CUT_VARIANTS=$v run $i: $(grep 'Time Cost\|Total Groups' $O/cli_v${v}_$i.out | tr '\n' ' ') dump $(grep -E '^[0-9]+ [0-9.]+: ' $O/cli_v${v}_$i.out | sha256sum | cut -c1-16)"
+done; done
